@@ -1,0 +1,131 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/ttsa.h declares, and its host
+logic (mel basis, pseudo-inverse, batch layout, argument/ config errors) matches the oracle.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import MAIN_AUDIO, ROOT, TEST_AUDIO
+from oracle.audio_oracle import OracleAudioProcessor, lr_mel
+
+import your_voice_tts_b200 as pkg
+from your_voice_tts_b200 import AudioProcessor, _lib as L
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ttsa.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ttsa_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 24
+    assert declared == set(L.PROTOTYPES), declared ^ set(L.PROTOTYPES)
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ttsa_version() == 100
+
+
+def _host_plan(audio):
+    ap = AudioProcessor(verbose=False, **audio)
+    return ap, ap._plan(host_only=True)
+
+
+@pytest.mark.parametrize("audio", [MAIN_AUDIO, TEST_AUDIO, dict(MAIN_AUDIO, sample_rate=16000),
+                                   dict(MAIN_AUDIO, sample_rate=24000, mel_fmax=None, mel_fmin=50.0)])
+def test_mel_basis_and_pinv_match_oracle(audio):
+    ap = AudioProcessor(verbose=False, **audio)
+    orc = OracleAudioProcessor(**audio)
+    M = ap._build_mel_basis()
+    np.testing.assert_allclose(M, orc._build_mel_basis(), atol=1e-14)
+    P = ap._inv_mel_basis()
+    Pref = np.linalg.pinv(orc._build_mel_basis())
+    assert P.shape == Pref.shape == (1025, audio["num_mels"])
+    np.testing.assert_allclose(P, Pref, atol=1e-10 * np.abs(Pref).max())
+
+
+def test_mel_basis_matches_reference_shim_golden(golden):
+    ap = AudioProcessor(verbose=False, **MAIN_AUDIO)
+    np.testing.assert_allclose(ap._build_mel_basis(), golden["main_mel_basis"], atol=2e-7)
+
+
+def test_pinv_rank_deficient_basis():
+    # 128 mels over 0-2 kHz at n_fft 2048: the lowest filters fall between bins -> all-zero rows, rank < num_mels
+    audio = dict(MAIN_AUDIO, num_mels=128, mel_fmax=1200.0)
+    M = lr_mel(22050, 2048, 128, 0.0, 1200.0)
+    assert np.linalg.matrix_rank(M) < 128
+    ap = AudioProcessor(verbose=False, **audio)
+    P = ap._inv_mel_basis()
+    Pref = np.linalg.pinv(M)
+    np.testing.assert_allclose(P, Pref, atol=1e-7 * np.abs(Pref).max())
+
+
+def test_batch_layout_from_frames_and_lengths():
+    ap, plan = _host_plan(MAIN_AUDIO)
+    lay = pkg.BatchLayout(plan, n_frames=[482, 1, 0, 5, 153])
+    assert lay.total_frames == 641
+    assert list(lay.frame_off) == [0, 482, 483, 483, 488, 641]
+    assert list(lay.wav_len) == [275 * 481, 0, 0, 275 * 4, 275 * 152]
+    assert all(o % 4 == 0 for o in lay.wav_off)
+    assert all(lay.wav_off[u + 1] - lay.wav_off[u] >= lay.wav_len[u] for u in range(5))
+    lay2 = pkg.BatchLayout(plan, wav_lengths=[132300, 41885, 1, 274, 275])
+    assert list(lay2.n_frames) == [482, 153, 1, 1, 2]          # T = 1 + L // hop
+    assert lay2.total_samples >= 132300 + 41885 + 1 + 274 + 275
+
+
+def test_error_codes_and_messages():
+    lib = L.load()
+    ap, plan = _host_plan(MAIN_AUDIO)
+    # a host-only plan has no compute path: loud failure, not a CPU fallback
+    lay = pkg.BatchLayout(plan, n_frames=[4])
+    rc = lib.ttsa_stft(plan.handle, lay.handle, None, None, None)
+    assert rc == L.TTSA_ERR_NO_DEVICE and b"no CPU path" in lib.ttsa_last_error()
+    rc = lib.ttsa_pointwise(plan.handle, 0, None, None, 4, None)
+    assert rc == L.TTSA_ERR_NO_DEVICE
+    # config validation
+    with pytest.raises(L.TtsaError) as ei:
+        AudioProcessor(verbose=False, **dict(MAIN_AUDIO, num_freq=513))._plan(host_only=True)
+    assert ei.value.code == L.TTSA_ERR_UNSUPPORTED
+    with pytest.raises(AssertionError):     # utils/audio.py:70-71
+        AudioProcessor(verbose=False, **dict(MAIN_AUDIO, mel_fmax=12000.0))._build_mel_basis()
+    c = L.TtsaConfig()
+    h = ctypes.c_void_p()
+    assert lib.ttsa_plan_create(ctypes.byref(c), -1, ctypes.byref(h)) == L.TTSA_ERR_BAD_CONFIG
+    assert lib.ttsa_plan_create(None, -1, ctypes.byref(h)) == L.TTSA_ERR_BAD_ARG
+    bad = np.array([-3], dtype=np.int32)
+    hb = ctypes.c_void_p()
+    rc = lib.ttsa_batch_from_frames(plan.handle, bad.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 1, ctypes.byref(hb))
+    assert rc == L.TTSA_ERR_BAD_ARG
+
+
+def test_audio_processor_attributes_and_prints(capsys):
+    ap = AudioProcessor(**TEST_AUDIO)
+    out = capsys.readouterr().out
+    assert " > Setting up Audio Processor..." in out and " | > hop_length:275" in out
+    assert (ap.n_fft, ap.hop_length, ap.win_length) == (2048, 275, 1102)
+    assert ap.max_norm == 4.0 and isinstance(ap.max_norm, float) and ap.mel_fmin == 95 and ap.clip_norm is True
+    ap2 = AudioProcessor(verbose=False, **dict(MAIN_AUDIO, mel_fmin=None, max_norm=None))
+    assert ap2.mel_fmin == 0 and ap2.max_norm == 1.0
+    with pytest.raises(RuntimeError):       # utils/audio.py:129-130
+        AudioProcessor(verbose=False, **dict(MAIN_AUDIO, preemphasis=0.0)).apply_preemphasis(np.zeros(8))
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ap = AudioProcessor(verbose=False, **MAIN_AUDIO)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ap.spectrogram(np.zeros(4000, dtype=np.float32))
+
+
+def test_host_helpers_match_reference_formulas(golden):
+    ap = AudioProcessor(verbose=False, **MAIN_AUDIO)
+    orc = OracleAudioProcessor(**MAIN_AUDIO)
+    x = np.linspace(-1, 1, 101)
+    np.testing.assert_array_equal(ap.mulaw_encode(x, 9), orc.mulaw_encode(x, 9))
+    np.testing.assert_allclose(ap.mulaw_decode(x, 9), orc.mulaw_decode(x, 9))
+    assert ap.encode_16bits(np.array([0.5, -1.0, 1.0])).tolist() == [16384, -32768, 32767]
+    np.testing.assert_allclose(ap.dequantize(ap.quantize(x, 9), 9), x, atol=1e-12)
+    wav = golden["wav_i16"].astype(np.float64) / 32768.0
+    assert ap.find_endpoint(wav) == orc.find_endpoint(wav)

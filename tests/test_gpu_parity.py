@@ -1,0 +1,255 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the drop-in AudioProcessor) against the float64 oracle
+and the committed fixtures.  Tolerances are the north-star's: forward STFT/mel within 1e-4, Griffin-Lim >= 60 dB
+waveform SNR with identically injected phases, spectral convergence matched per iteration (1e-3 relative)."""
+import numpy as np
+import pytest
+
+from conftest import MAIN_AUDIO, TEST_AUDIO, run_reference_test_normalize, snr_db, synth_speech_like
+from oracle.audio_oracle import OracleAudioProcessor, lfilter_fir2, lfilter_iir1, lr_istft, lr_stft
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-4       # north_star: forward STFT / mel within 1e-4 (max-abs on normalised output, per unit max_norm)
+GL_SNR_DB = 60.0     # north_star: >= 60 dB waveform SNR vs the float64 reference
+SC_RTOL = 1e-3
+
+
+def _ap(audio):
+    from your_voice_tts_b200 import AudioProcessor
+    return AudioProcessor(verbose=False, **audio)
+
+
+def _wav(golden):
+    return golden["wav_i16"].astype(np.float64) / 32768.0
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+# ------------------------------------------------------------------------------------------------ forward
+@pytest.mark.parametrize("name", ["test", "main"])
+def test_spectrogram_and_mel_vs_oracle_and_golden(golden, golden_audio_cfgs, name):
+    audio = golden_audio_cfgs[name]
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    wav = _wav(golden)
+    lin, mel = ap.spectrogram(wav), ap.melspectrogram(wav)
+    lin_o, mel_o = orc.spectrogram(wav.astype(np.float32)), orc.melspectrogram(wav.astype(np.float32))
+    assert lin.shape == (1025, 153) and mel.shape == (80, 153) and lin.dtype == np.float32
+    assert np.abs(lin - lin_o).max() <= FWD_TOL * ap.max_norm
+    assert np.abs(mel - mel_o).max() <= FWD_TOL * ap.max_norm
+    # fixtures produced by the reference's own utils/audio.py (librosa shimmed by torch)
+    assert np.abs(lin[:, ::4] - golden[f"{name}_lin_sub4"]).max() <= FWD_TOL * ap.max_norm
+    assert np.abs(mel - golden[f"{name}_mel"]).max() <= FWD_TOL * ap.max_norm
+
+
+@pytest.mark.parametrize("hop_win_sr", [(275, 1102, 22050), (200, 800, 16000), (300, 1200, 24000)])
+def test_stft_istft_vs_oracle(hop_win_sr):
+    hop, win, sr = hop_win_sr
+    ap = _ap(dict(MAIN_AUDIO, sample_rate=sr))
+    assert (ap.hop_length, ap.win_length) == (hop, win)
+    y = np.random.default_rng(3).standard_normal(hop * 37 + 11).astype(np.float32)
+    D = ap._stft(y)
+    Do = lr_stft(y, 2048, hop, win)
+    assert D.shape == Do.shape and D.dtype == np.complex64
+    assert np.linalg.norm(D - Do) / np.linalg.norm(Do) <= 1e-5          # normwise (1e-4 bar, fp32 gives ~1e-7)
+    assert np.abs(D - Do).max() <= 1e-4 * np.abs(Do).max()
+    yi = ap._istft(Do.astype(np.complex64))
+    yo = lr_istft(Do.astype(np.complex64), hop, win)
+    assert yi.shape == yo.shape == (hop * (Do.shape[1] - 1),)
+    assert snr_db(yo, yi) >= 100.0
+    # analysis -> synthesis round trip (size-independent property)
+    assert snr_db(y[:len(yi)], ap._istft(D)) >= 100.0
+
+
+def test_stft_edge_lengths():
+    ap = _ap(MAIN_AUDIO)
+    for n in (1, 2, 3, 274, 275, 276, 1023, 1025, 2049):
+        y = np.random.default_rng(n).standard_normal(n).astype(np.float32)
+        D = ap._stft(y)
+        Do = lr_stft(y, 2048, 275, 1102) if n >= 2 else None
+        assert D.shape == (1025, 1 + n // 275)
+        if Do is not None:
+            assert np.abs(D - Do).max() <= 1e-4 * max(1.0, np.abs(Do).max()), n
+
+
+# ------------------------------------------------------------------------------------------------ Griffin-Lim
+@pytest.mark.parametrize("name", ["test", "main"])
+def test_griffin_lim_vs_oracle_and_golden(golden, golden_audio_cfgs, name):
+    audio = golden_audio_cfgs[name]
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    lin_x, mel_x = golden[f"{name}_gl_lin_in"], golden[f"{name}_gl_mel_in"]
+    angles = (2.0 * np.pi * np.random.RandomState(1234).rand(*lin_x.shape)).astype(np.float32)
+    y, sc = ap.inv_spectrogram(lin_x, init_angles=angles, return_sc=True)
+    yo, sco = orc.inv_spectrogram(lin_x, init_angles=angles, return_sc=True)
+    assert y.shape == yo.shape == (275 * 39,)
+    assert snr_db(yo, y) >= GL_SNR_DB, snr_db(yo, y)
+    np.testing.assert_allclose(sc, sco, rtol=SC_RTOL)
+    # the reference's own run (np.random.seed(1234) phases in float64; ours are the float32 rounding of the same draw)
+    assert snr_db(golden[f"{name}_inv_spectrogram"], y) >= GL_SNR_DB
+    ym, scm = ap.inv_mel_spectrogram(mel_x, init_angles=angles, return_sc=True)
+    ymo, scmo = orc.inv_mel_spectrogram(mel_x, init_angles=angles, return_sc=True)
+    assert snr_db(ymo, ym) >= GL_SNR_DB, snr_db(ymo, ym)
+    np.testing.assert_allclose(scm, scmo, rtol=SC_RTOL)
+    assert snr_db(golden[f"{name}_inv_mel_spectrogram"], ym) >= GL_SNR_DB
+
+
+def test_griffin_lim_reference_rng_draw(golden):
+    """Without injected phases the reference's np.random.rand draw is reproduced (utils/audio.py:183)."""
+    ap, orc = _ap(MAIN_AUDIO), OracleAudioProcessor(**MAIN_AUDIO)
+    lin_x = golden["main_gl_lin_in"]
+    np.random.seed(99)
+    y = ap.inv_spectrogram(lin_x)
+    np.random.seed(99)
+    yo = orc.inv_spectrogram(lin_x)
+    assert snr_db(yo, y) >= GL_SNR_DB
+
+
+def test_griffin_lim_magnitude_input_and_full_length_utterance():
+    """_griffin_lim(S) on a 6 s LJSpeech-shape spectrogram (T = 482), configs[0] of BASELINE.json at 8 iterations."""
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=8)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    wav = synth_speech_like(1234)
+    spec = orc.spectrogram(wav).astype(np.float32)
+    assert spec.shape == (1025, 482)
+    S = (orc._db_to_amp(orc._denormalize(spec.astype(np.float64)) + orc.ref_level_db) ** orc.power).astype(np.float32)
+    angles = (2 * np.pi * np.random.default_rng(5).random(S.shape)).astype(np.float32)
+    y, sc = ap._griffin_lim(S, init_angles=angles, return_sc=True)
+    yo, sco = orc._griffin_lim(S, init_angles=angles, return_sc=True)
+    assert y.shape == (132275,)
+    assert snr_db(yo, y) >= GL_SNR_DB, snr_db(yo, y)
+    np.testing.assert_allclose(sc, sco, rtol=SC_RTOL)
+
+
+def test_ragged_batch_matches_per_utterance_oracle():
+    """Variable-length packed batch (T in {2, 5, 9, 40, 61, 153}): every utterance equals its own oracle run."""
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=5)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    Ts = [40, 2, 153, 5, 9, 61, 1]
+    rng = np.random.default_rng(11)
+    specs = [rng.random((T, 1025)).astype(np.float32) for T in Ts]         # packed layout is frame-major
+    angs = [(2 * np.pi * rng.random((T, 1025))).astype(np.float32) for T in Ts]
+    lay = ap.layout(n_frames=Ts)
+    dev = torch.device("cuda")
+    out, sc = ap.inv_spectrogram_batch(torch.from_numpy(np.concatenate(specs)).to(dev), lay,
+                                       init_angles=torch.from_numpy(np.concatenate(angs)).to(dev), return_sc=True)
+    outs = [o.cpu().numpy() for o in lay.split_wav(out)]
+    sc = sc.cpu().numpy()
+    for u, T in enumerate(Ts):
+        assert outs[u].shape == (275 * max(0, T - 1),)
+        if T < 2:
+            continue
+        yo, sco = orc.inv_spectrogram(specs[u].T, init_angles=angs[u].T, return_sc=True)
+        assert snr_db(yo, outs[u]) >= GL_SNR_DB, (T, snr_db(yo, outs[u]))
+        np.testing.assert_allclose(sc[:, u], sco, rtol=SC_RTOL)
+
+
+def test_large_batch_segments_deterministic_and_match_oracle():
+    """64 x T=482 (BASELINE configs[1] shape): CTAs own multi-tile segments with warm-up frames.  Checked by
+    determinism, by comparing two utterances against the oracle, and by batch-composition independence."""
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=3)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    B, T = 64, 482
+    g = torch.Generator(device="cuda").manual_seed(0)
+    spec = torch.rand((B * T, 1025), device="cuda", generator=g)
+    ang = torch.rand((B * T, 1025), device="cuda", generator=g) * (2 * np.pi)
+    lay = ap.layout(n_frames=[T] * B)
+    y1 = ap.inv_spectrogram_batch(spec, lay, init_angles=ang).clone()
+    y2 = ap.inv_spectrogram_batch(spec, lay, init_angles=ang)
+    assert torch.equal(y1, y2)                                         # no atomics on the data path
+    for u in (0, 37):
+        yo = orc.inv_spectrogram(spec[u * T:(u + 1) * T].cpu().numpy().T, init_angles=ang[u * T:(u + 1) * T].cpu().numpy().T)
+        yu = lay.split_wav(y1)[u].cpu().numpy()
+        assert snr_db(yo, yu) >= GL_SNR_DB, (u, snr_db(yo, yu))
+    # the same utterance inside a different batch gives the same samples (different CTA partition) to fp32 rounding
+    lay1 = ap.layout(n_frames=[T])
+    y_single = ap.inv_spectrogram_batch(spec[37 * T:38 * T].contiguous(), lay1, init_angles=ang[37 * T:38 * T].contiguous())
+    assert snr_db(lay.split_wav(y1)[37].cpu().numpy(), y_single[:275 * (T - 1)].cpu().numpy()) >= 120.0
+
+
+def test_device_rng_phases():
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=6)
+    ap = _ap(audio)
+    T = 40
+    spec = torch.rand((T, 1025), device="cuda")
+    lay = ap.layout(n_frames=[T])
+    a, sc = ap.inv_spectrogram_batch(spec, lay, seed=7, return_sc=True)
+    b = ap.inv_spectrogram_batch(spec, lay, seed=7)
+    c = ap.inv_spectrogram_batch(spec, lay, seed=8)
+    assert torch.isfinite(a).all() and torch.equal(a, b) and not torch.equal(a, c)
+    sc = sc.cpu().numpy()[:, 0]
+    assert sc[-1] < sc[0]
+
+
+# ------------------------------------------------------------------------------------------------ mel <-> linear
+def test_mel_linear_projections(golden):
+    ap, orc = _ap(MAIN_AUDIO), OracleAudioProcessor(**MAIN_AUDIO)
+    rng = np.random.default_rng(2)
+    S = rng.random((1025, 33)).astype(np.float32) * 3.0
+    m, mo = ap._linear_to_mel(S), orc._linear_to_mel(S.astype(np.float64))
+    assert m.shape == (80, 33)
+    np.testing.assert_allclose(m, mo, rtol=2e-6, atol=1e-7)
+    mel_amp = (rng.random((80, 33)) * 2.0).astype(np.float32)
+    lin, lino = ap._mel_to_linear(mel_amp), orc._mel_to_linear(mel_amp.astype(np.float64))
+    assert lin.shape == (1025, 33) and lin.min() >= 1e-10
+    np.testing.assert_allclose(lin, lino, rtol=1e-4, atol=2e-5)
+    spec = orc.spectrogram(_wav(golden)).astype(np.float32)
+    l2m = ap.out_linear_to_mel(spec)
+    assert np.abs(l2m - orc.out_linear_to_mel(spec)).max() <= FWD_TOL
+    assert np.abs(l2m - golden["main_lin2mel"]).max() <= FWD_TOL
+
+
+# ------------------------------------------------------------------------------------------------ filters / elementwise
+@pytest.mark.parametrize("p", [0.97, 0.98])
+def test_pre_and_de_emphasis(p):
+    ap = _ap(dict(MAIN_AUDIO, preemphasis=p))
+    for n in (1, 7, 2048, 2049, 132275):
+        x = np.random.default_rng(n).standard_normal(n).astype(np.float32)
+        np.testing.assert_allclose(ap.apply_preemphasis(x), lfilter_fir2(x, p), atol=2e-6)
+        yo = lfilter_iir1(x, p)
+        y = ap.apply_inv_preemphasis(x)
+        assert y.shape == yo.shape
+        assert snr_db(yo, y) >= 100.0, (n, snr_db(yo, y))
+
+
+def test_reference_test_normalize_on_gpu(golden):
+    """The reference's tests/test_audio.py:57-144, run against the drop-in class (attributes mutated live)."""
+    run_reference_test_normalize(_ap(TEST_AUDIO), _wav(golden))
+
+
+def test_pointwise_vs_oracle():
+    x = (np.random.default_rng(0).random((80, 50)) * 140.0 - 120.0).astype(np.float32)
+    for audio in (MAIN_AUDIO, TEST_AUDIO, dict(TEST_AUDIO, clip_norm=False), dict(MAIN_AUDIO, signal_norm=False)):
+        ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+        n = ap._normalize(x)
+        np.testing.assert_allclose(n, orc._normalize(x.astype(np.float64)), atol=2e-6 * ap.max_norm)
+        np.testing.assert_allclose(ap._denormalize(n), orc._denormalize(n.astype(np.float64)), atol=2e-4)
+        amp = ap._db_to_amp(x * 0.5)
+        np.testing.assert_allclose(amp, orc._db_to_amp(x.astype(np.float64) * 0.5), rtol=5e-6)
+        np.testing.assert_allclose(ap._amp_to_db(amp), orc._amp_to_db(amp.astype(np.float64)), atol=2e-5)
+
+
+def test_reference_audio_synthesis_matrix(golden, tmp_path):
+    """Mirror of tests/test_audio.py:23-55 (wav -> mel -> wav for 10 normalisation settings, 30 GL iterations)."""
+    ap = _ap(TEST_AUDIO)
+    wav = _wav(golden)[:275 * 60]
+    for max_norm in (1.0, 4.0):
+        for signal_norm, symmetric_norm, clip_norm in [(False, False, False), (True, False, False), (True, True, False),
+                                                       (True, False, True), (True, True, True)]:
+            ap.max_norm, ap.signal_norm, ap.symmetric_norm, ap.clip_norm = max_norm, signal_norm, symmetric_norm, clip_norm
+            mel = ap.melspectrogram(wav)
+            wav_ = ap.inv_mel_spectrogram(mel)
+            assert wav_.shape == (275 * (mel.shape[1] - 1),) and np.isfinite(wav_).all() and np.abs(wav_).max() > 1e-3
+            ap.save_wav(wav_, str(tmp_path / "out.wav"))
+
+
+def test_tensor_in_tensor_out():
+    ap = _ap(MAIN_AUDIO)
+    y = torch.randn(275 * 20, device="cuda")
+    S = ap.spectrogram(y)
+    assert isinstance(S, torch.Tensor) and S.is_cuda and S.shape == (1025, 21)
+    w = ap.inv_spectrogram(S)
+    assert isinstance(w, torch.Tensor) and w.shape == (275 * 20,)

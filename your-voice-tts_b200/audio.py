@@ -1,0 +1,568 @@
+"""Drop-in ``AudioProcessor`` (reference: utils/audio.py:11-255) whose arithmetic runs in libttsa_b200.so.
+
+Same constructor keywords (the ``audio`` block of config.json:5-25), same public attributes (mutable between
+calls, as tests/test_audio.py:32-35 does), same method names and array conventions: single utterance, numpy in,
+numpy out, spectrograms as ``[D, T]``.  Every method that touches signal data launches this repo's CUDA kernels
+through the C ABI (include/ttsa.h); PyTorch only owns device memory and the stream.  There is no CPU path: without
+the compiled library or without a B200 the compute methods raise.
+
+Additive API (not in the reference): ``*_batch`` methods taking/returning packed frame-major CUDA tensors,
+``init_angles=`` / ``seed=`` for reproducible Griffin-Lim phases, ``return_sc=`` for the per-iteration spectral
+convergence, ``device=`` and ``verbose=`` constructor keywords.
+"""
+import ctypes
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib as L
+
+__all__ = ["AudioProcessor", "BatchLayout"]
+
+_PLAN_CACHE = OrderedDict()
+_PLAN_CACHE_MAX = 32
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class _Plan(object):
+    """Owns one ttsa_plan handle (immutable per (config, device))."""
+
+    def __init__(self, cfg_tuple, device_index):
+        lib = L.load()
+        c = L.TtsaConfig()
+        (c.sample_rate, c.num_mels, c.num_freq, c.n_fft, c.hop_length, c.win_length, c.signal_norm, c.symmetric_norm,
+         c.clip_norm, c.griffin_lim_iters, c.min_level_db, c.ref_level_db, c.power, c.preemphasis, c.max_norm,
+         c.mel_fmin, c.mel_fmax) = cfg_tuple
+        self.cfg = c
+        self.device_index = device_index
+        h = ctypes.c_void_p()
+        L.check(lib.ttsa_plan_create(ctypes.byref(c), device_index, ctypes.byref(h)))
+        self.handle = h
+        self.lib = lib
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.ttsa_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class BatchLayout(object):
+    """Packed layout of a batch of utterances (ttsa_batch): frame counts, waveform lengths and offsets."""
+
+    def __init__(self, plan, n_frames=None, wav_lengths=None):
+        assert (n_frames is None) != (wav_lengths is None)
+        self.plan = plan
+        lib = plan.lib
+        src = n_frames if n_frames is not None else wav_lengths
+        arr = np.ascontiguousarray(np.asarray(src, dtype=np.int32).reshape(-1))
+        self.n_utts = int(arr.shape[0])
+        h = ctypes.c_void_p()
+        fn = lib.ttsa_batch_from_frames if n_frames is not None else lib.ttsa_batch_from_wav_lengths
+        L.check(fn(plan.handle, arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), self.n_utts, ctypes.byref(h)))
+        self.handle = h
+        self.total_frames = int(lib.ttsa_batch_total_frames(h))
+        self.total_samples = int(lib.ttsa_batch_total_samples(h))
+        fo = np.zeros(self.n_utts + 1, dtype=np.int64)
+        wo = np.zeros(self.n_utts + 1, dtype=np.int64)
+        wl = np.zeros(self.n_utts, dtype=np.int32)
+        L.check(lib.ttsa_batch_offsets(h, fo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                       wo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                       wl.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        self.frame_off, self.wav_off, self.wav_len = fo, wo, wl
+        self.n_frames = np.diff(fo).astype(np.int64)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.plan.lib.ttsa_batch_destroy(self.handle)
+        except Exception:
+            pass
+
+    def split_wav(self, packed):
+        """Views of the packed waveform buffer, one per utterance."""
+        return [packed[int(self.wav_off[u]):int(self.wav_off[u]) + int(self.wav_len[u])] for u in range(self.n_utts)]
+
+    def split_frames(self, packed):
+        return [packed[int(self.frame_off[u]):int(self.frame_off[u + 1])] for u in range(self.n_utts)]
+
+
+class AudioProcessor(object):
+    def __init__(self,
+                 sample_rate=None,
+                 num_mels=None,
+                 min_level_db=None,
+                 frame_shift_ms=None,
+                 frame_length_ms=None,
+                 ref_level_db=None,
+                 num_freq=None,
+                 power=None,
+                 preemphasis=None,
+                 signal_norm=None,
+                 symmetric_norm=None,
+                 max_norm=None,
+                 mel_fmin=None,
+                 mel_fmax=None,
+                 clip_norm=True,
+                 griffin_lim_iters=None,
+                 do_trim_silence=False,
+                 device=None,
+                 verbose=True,
+                 **kwargs):
+        if verbose:
+            print(" > Setting up Audio Processor...")
+        # utils/audio.py:34-51
+        self.sample_rate = sample_rate
+        self.num_mels = num_mels
+        self.min_level_db = min_level_db
+        self.frame_shift_ms = frame_shift_ms
+        self.frame_length_ms = frame_length_ms
+        self.ref_level_db = ref_level_db
+        self.num_freq = num_freq
+        self.power = power
+        self.preemphasis = preemphasis
+        self.griffin_lim_iters = griffin_lim_iters
+        self.signal_norm = signal_norm
+        self.symmetric_norm = symmetric_norm
+        self.mel_fmin = 0 if mel_fmin is None else mel_fmin
+        self.mel_fmax = mel_fmax
+        self.max_norm = 1.0 if max_norm is None else float(max_norm)
+        self.clip_norm = clip_norm
+        self.do_trim_silence = do_trim_silence
+        self.n_fft, self.hop_length, self.win_length = self._stft_parameters()
+        if verbose:
+            members = vars(self)
+            for key, value in members.items():
+                print(" | > {}:{}".format(key, value))
+        self._device = device
+        self._batch_cache = OrderedDict()
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    def _stft_parameters(self):
+        """utils/audio.py:114-119"""
+        n_fft = (self.num_freq - 1) * 2
+        hop_length = int(self.frame_shift_ms / 1000.0 * self.sample_rate)
+        win_length = int(self.frame_length_ms / 1000.0 * self.sample_rate)
+        return n_fft, hop_length, win_length
+
+    def _cfg_tuple(self):
+        # parameters are read at call time: the reference's tests mutate them on a live object
+        n_fft = (self.num_freq - 1) * 2
+        return (int(self.sample_rate), int(self.num_mels), int(self.num_freq), int(n_fft), int(self.hop_length),
+                int(self.win_length), int(bool(self.signal_norm)), int(bool(self.symmetric_norm)),
+                int(bool(self.clip_norm)), int(self.griffin_lim_iters or 0), float(self.min_level_db),
+                float(self.ref_level_db), float(self.power), float(self.preemphasis or 0.0), float(self.max_norm),
+                float(self.mel_fmin or 0.0), float(self.mel_fmax) if self.mel_fmax is not None else -1.0)
+
+    def _device_index(self):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("AudioProcessor needs a CUDA device (B200, sm_100a): the audio hot path has no CPU "
+                               "implementation in this package")
+        dev = self._device
+        if dev is None:
+            return torch.cuda.current_device()
+        dev = torch.device(dev)
+        return dev.index if dev.index is not None else torch.cuda.current_device()
+
+    def _plan(self, host_only=False):
+        if self.mel_fmax is not None:
+            assert self.mel_fmax <= self.sample_rate // 2          # utils/audio.py:70-71
+        key = (self._cfg_tuple(), -1 if host_only else self._device_index())
+        plan = _PLAN_CACHE.get(key)
+        if plan is None:
+            plan = _Plan(*key)
+            _PLAN_CACHE[key] = plan
+            while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+                _PLAN_CACHE.popitem(last=False)
+        else:
+            _PLAN_CACHE.move_to_end(key)
+        return plan
+
+    def layout(self, n_frames=None, wav_lengths=None):
+        """BatchLayout for utterances given by frame counts (spectrogram inputs) or by waveform lengths."""
+        plan = self._plan()
+        src = n_frames if n_frames is not None else wav_lengths
+        key = (id(plan), n_frames is not None, tuple(int(v) for v in np.asarray(src).reshape(-1)))
+        lay = self._batch_cache.get(key)
+        if lay is None:
+            lay = BatchLayout(plan, n_frames=n_frames, wav_lengths=wav_lengths)
+            self._batch_cache[key] = lay
+            while len(self._batch_cache) > 16:
+                self._batch_cache.popitem(last=False)
+        return lay
+
+    def _dev(self):
+        return _torch().device("cuda", self._device_index())
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+    def _to_dev(self, x, dtype=None):
+        torch = _torch()
+        if isinstance(x, torch.Tensor):
+            t = x.to(device=self._dev(), dtype=dtype or torch.float32)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32))).to(self._dev())
+        return t.contiguous()
+
+    def _transpose(self, t):
+        """[R, C] -> [C, R] with the library's own kernel (layout shim for the reference's [D, T] arrays)."""
+        torch = _torch()
+        rows, cols = t.shape
+        out = torch.empty((cols, rows), dtype=torch.float32, device=t.device)
+        L.check(L.load().ttsa_transpose(self._ptr(t), self._ptr(out), rows, cols, self._stream()))
+        return out
+
+    @staticmethod
+    def _is_tensor(x):
+        torch = _torch()
+        return isinstance(x, torch.Tensor)
+
+    def _ret(self, t, like):
+        """Return numpy for numpy callers (the reference's contract), tensors for tensor callers."""
+        if self._is_tensor(like):
+            return t
+        return t.cpu().numpy()
+
+    # ------------------------------------------------------------------------------------------ batched API
+    def features_batch(self, wav_packed, layout, want_linear=True, want_mel=True, preemphasis=None):
+        """spectrogram() and melspectrogram() of every utterance in one pass (utils/audio.py:138-152).
+
+        wav_packed: CUDA float32 [layout.total_samples]; returns (linear [sum_T, num_freq] | None, mel [sum_T, num_mels] | None).
+        """
+        torch = _torch()
+        plan = layout.plan
+        lin = torch.empty((layout.total_frames, self.num_freq), dtype=torch.float32, device=wav_packed.device) if want_linear else None
+        mel = torch.empty((layout.total_frames, self.num_mels), dtype=torch.float32, device=wav_packed.device) if want_mel else None
+        pre = (self.preemphasis != 0) if preemphasis is None else bool(preemphasis)
+        L.check(plan.lib.ttsa_stft_features(plan.handle, layout.handle, self._ptr(wav_packed), self._ptr(lin),
+                                            self._ptr(mel), L.FEAT_PREEMPHASIS if pre else 0, self._stream()))
+        return lin, mel
+
+    def stft_batch(self, wav_packed, layout):
+        torch = _torch()
+        plan = layout.plan
+        out = torch.empty((layout.total_frames, self.num_freq, 2), dtype=torch.float32, device=wav_packed.device)
+        L.check(plan.lib.ttsa_stft(plan.handle, layout.handle, self._ptr(wav_packed), self._ptr(out), self._stream()))
+        return out
+
+    def istft_batch(self, stft_packed, layout):
+        torch = _torch()
+        plan = layout.plan
+        out = torch.zeros((max(1, layout.total_samples),), dtype=torch.float32, device=stft_packed.device)
+        L.check(plan.lib.ttsa_istft(plan.handle, layout.handle, self._ptr(stft_packed), self._ptr(out), self._stream()))
+        return out
+
+    def griffin_lim_batch(self, spec_packed, layout, spec_kind=L.SPEC_MAGNITUDE, init_angles=None, seed=0,
+                          deemphasis=False, return_sc=False, iters=None, out=None, workspace=None):
+        """_griffin_lim over a packed batch (utils/audio.py:182-189).  Returns the packed waveform buffer
+        (and, with return_sc, the [iters, B] spectral-convergence log)."""
+        torch = _torch()
+        plan = layout.plan
+        iters = int(self.griffin_lim_iters if iters is None else iters)
+        dev = spec_packed.device
+        if out is None:
+            out = torch.zeros((max(1, layout.total_samples),), dtype=torch.float32, device=dev)
+        ws_bytes = int(plan.lib.ttsa_griffin_lim_workspace_bytes(plan.handle, layout.handle))
+        if workspace is None:
+            workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        sc = torch.empty((max(1, iters), layout.n_utts, 2), dtype=torch.float32, device=dev) if return_sc else None
+        L.check(plan.lib.ttsa_griffin_lim(plan.handle, layout.handle, self._ptr(spec_packed), int(spec_kind), iters,
+                                          self._ptr(init_angles), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                          L.GL_DEEMPHASIS if deemphasis else 0, self._ptr(out), self._ptr(sc),
+                                          self._ptr(workspace), workspace.numel(), self._stream()))
+        if return_sc:
+            sc_val = torch.sqrt(sc[:iters, :, 0] / sc[:iters, :, 1].clamp_min(1e-30))
+            return out, sc_val
+        return out
+
+    def mel_to_linear_batch(self, mel_packed, layout, in_kind=L.MEL_IN_AMPLITUDE, out_kind=L.MEL_OUT_PLAIN):
+        torch = _torch()
+        plan = layout.plan
+        out = torch.empty((layout.total_frames, self.num_freq), dtype=torch.float32, device=mel_packed.device)
+        L.check(plan.lib.ttsa_mel_to_linear(plan.handle, layout.handle, self._ptr(mel_packed), in_kind,
+                                            self._ptr(out), out_kind, self._stream()))
+        return out
+
+    def linear_to_mel_batch(self, lin_packed, layout, in_kind=L.MEL_IN_AMPLITUDE, out_kind=L.MEL_OUT_PLAIN):
+        torch = _torch()
+        plan = layout.plan
+        out = torch.empty((layout.total_frames, self.num_mels), dtype=torch.float32, device=lin_packed.device)
+        L.check(plan.lib.ttsa_linear_to_mel(plan.handle, layout.handle, self._ptr(lin_packed), in_kind,
+                                            self._ptr(out), out_kind, self._stream()))
+        return out
+
+    def inv_spectrogram_batch(self, spec_packed, layout, init_angles=None, seed=0, return_sc=False, out=None,
+                              workspace=None):
+        """inv_spectrogram for a packed batch of normalised linear spectrograms [sum_T, num_freq]."""
+        return self.griffin_lim_batch(spec_packed, layout, L.SPEC_NORM_DB, init_angles, seed,
+                                      deemphasis=self.preemphasis != 0, return_sc=return_sc, out=out,
+                                      workspace=workspace)
+
+    def inv_mel_spectrogram_batch(self, mel_packed, layout, init_angles=None, seed=0, return_sc=False, out=None,
+                                  workspace=None):
+        """inv_mel_spectrogram for a packed batch of normalised mel spectrograms [sum_T, num_mels]."""
+        S = self.mel_to_linear_batch(mel_packed, layout, L.MEL_IN_NORM_DB, L.MEL_OUT_POWER)
+        return self.griffin_lim_batch(S, layout, L.SPEC_MAGNITUDE, init_angles, seed,
+                                      deemphasis=self.preemphasis != 0, return_sc=return_sc, out=out,
+                                      workspace=workspace)
+
+    # ------------------------------------------------------------------------------------------ reference API
+    def save_wav(self, wav, path):
+        """utils/audio.py:56-58"""
+        from scipy.io import wavfile
+        wav = np.asarray(wav)
+        wav_norm = wav * (32767 / max(0.01, np.max(np.abs(wav))))
+        wavfile.write(path, self.sample_rate, wav_norm.astype(np.int16))
+
+    def _build_mel_basis(self):
+        """utils/audio.py:68-77 (librosa.filters.mel semantics), float64 [num_mels, num_freq]."""
+        plan = self._plan(host_only=True)
+        out = np.empty((self.num_mels, self.num_freq), dtype=np.float64)
+        L.check(plan.lib.ttsa_plan_mel_basis(plan.handle, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return out
+
+    def _inv_mel_basis(self):
+        plan = self._plan(host_only=True)
+        out = np.empty((self.num_freq, self.num_mels), dtype=np.float64)
+        L.check(plan.lib.ttsa_plan_inv_mel_basis(plan.handle, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return out
+
+    def _dt_in(self, x):
+        """[D, T] array/tensor -> packed frame-major CUDA tensor [T, D] + layout."""
+        t = self._to_dev(x)
+        if t.dim() != 2:
+            raise ValueError("expected a [D, T] spectrogram, got shape %s" % (tuple(t.shape),))
+        tt = self._transpose(t)
+        return tt, self.layout(n_frames=[tt.shape[0]])
+
+    def _linear_to_mel(self, spectrogram):
+        """utils/audio.py:60-62: np.dot(mel_basis, S); [num_freq, T] -> [num_mels, T]"""
+        tt, lay = self._dt_in(spectrogram)
+        out = self.linear_to_mel_batch(tt, lay)
+        return self._ret(self._transpose(out), spectrogram)
+
+    def _mel_to_linear(self, mel_spec):
+        """utils/audio.py:64-66: max(1e-10, pinv(mel_basis) @ mel); [num_mels, T] -> [num_freq, T]"""
+        tt, lay = self._dt_in(mel_spec)
+        out = self.mel_to_linear_batch(tt, lay)
+        return self._ret(self._transpose(out), mel_spec)
+
+    def _pointwise(self, op, x):
+        t = self._to_dev(x)
+        torch = _torch()
+        out = torch.empty_like(t)
+        plan = self._plan()
+        L.check(plan.lib.ttsa_pointwise(plan.handle, op, self._ptr(t), self._ptr(out), t.numel(), self._stream()))
+        return self._ret(out, x)
+
+    def _normalize(self, S):
+        """utils/audio.py:79-94"""
+        return self._pointwise(L.PW_NORMALIZE, S)
+
+    def _denormalize(self, S):
+        """utils/audio.py:96-112"""
+        return self._pointwise(L.PW_DENORMALIZE, S)
+
+    def _amp_to_db(self, x):
+        """utils/audio.py:121-123"""
+        return self._pointwise(L.PW_AMP_TO_DB, x)
+
+    def _db_to_amp(self, x):
+        """utils/audio.py:125-126"""
+        if np.isscalar(x):          # find_endpoint passes a python scalar (utils/audio.py:206)
+            return np.power(10.0, x * 0.05)
+        return self._pointwise(L.PW_DB_TO_AMP, x)
+
+    def _wav_in(self, x):
+        t = self._to_dev(x).reshape(-1)
+        return t, self.layout(wav_lengths=[t.shape[0]])
+
+    def apply_preemphasis(self, x):
+        """utils/audio.py:128-131"""
+        if self.preemphasis == 0:
+            raise RuntimeError(" !! Preemphasis is applied with factor 0.0. ")
+        t, lay = self._wav_in(x)
+        torch = _torch()
+        out = torch.empty_like(t)
+        L.check(lay.plan.lib.ttsa_preemphasis(lay.plan.handle, lay.handle, self._ptr(t), self._ptr(out), self._stream()))
+        return self._ret(out, x)
+
+    def apply_inv_preemphasis(self, x):
+        """utils/audio.py:133-136"""
+        if self.preemphasis == 0:
+            raise RuntimeError(" !! Preemphasis is applied with factor 0.0. ")
+        t, lay = self._wav_in(x)
+        torch = _torch()
+        out = torch.empty_like(t)
+        lib = lay.plan.lib
+        ws = torch.empty((int(lib.ttsa_deemphasis_workspace_bytes(lay.plan.handle, lay.handle)),), dtype=torch.uint8,
+                         device=t.device)
+        L.check(lib.ttsa_deemphasis(lay.plan.handle, lay.handle, self._ptr(t), self._ptr(out), self._ptr(ws),
+                                    ws.numel(), self._stream()))
+        return self._ret(out, x)
+
+    def spectrogram(self, y):
+        """utils/audio.py:138-144; [L] -> [num_freq, T]"""
+        t, lay = self._wav_in(y)
+        lin, _ = self.features_batch(t, lay, want_linear=True, want_mel=False)
+        return self._ret(self._transpose(lin), y)
+
+    def melspectrogram(self, y):
+        """utils/audio.py:146-152; [L] -> [num_mels, T]"""
+        t, lay = self._wav_in(y)
+        _, mel = self.features_batch(t, lay, want_linear=False, want_mel=True)
+        return self._ret(self._transpose(mel), y)
+
+    def _host_angles(self, shape_dt, init_angles):
+        """Initial phases as a packed [T, D] CUDA tensor.  Without injected phases the reference's own draw is
+        reproduced: 2*pi*np.random.rand(*S.shape) on the [D, T] array (utils/audio.py:183), consuming numpy's
+        global RNG exactly as the reference does."""
+        if init_angles is None:
+            init_angles = 2.0 * np.pi * np.random.rand(*shape_dt)
+        a = self._to_dev(np.asarray(init_angles, dtype=np.float32) if not self._is_tensor(init_angles) else init_angles)
+        return self._transpose(a)
+
+    def inv_spectrogram(self, spectrogram, init_angles=None, return_sc=False):
+        """utils/audio.py:154-162; normalised [num_freq, T] -> waveform [hop*(T-1)]"""
+        tt, lay = self._dt_in(spectrogram)
+        ang = self._host_angles(tuple(tt.shape[::-1]), init_angles)
+        out = self.inv_spectrogram_batch(tt, lay, init_angles=ang, return_sc=return_sc)
+        if return_sc:
+            return self._ret(out[0][:lay.wav_len[0]], spectrogram), self._ret(out[1][:, 0], spectrogram)
+        return self._ret(out[:lay.wav_len[0]], spectrogram)
+
+    def inv_mel_spectrogram(self, mel_spectrogram, init_angles=None, return_sc=False):
+        """utils/audio.py:164-172; normalised [num_mels, T] -> waveform [hop*(T-1)]"""
+        tt, lay = self._dt_in(mel_spectrogram)
+        ang = self._host_angles((self.num_freq, tt.shape[0]), init_angles)
+        out = self.inv_mel_spectrogram_batch(tt, lay, init_angles=ang, return_sc=return_sc)
+        if return_sc:
+            return self._ret(out[0][:lay.wav_len[0]], mel_spectrogram), self._ret(out[1][:, 0], mel_spectrogram)
+        return self._ret(out[:lay.wav_len[0]], mel_spectrogram)
+
+    def out_linear_to_mel(self, linear_spec):
+        """utils/audio.py:174-180; normalised [num_freq, T] -> normalised [num_mels, T]"""
+        tt, lay = self._dt_in(linear_spec)
+        out = self.linear_to_mel_batch(tt, lay, L.MEL_IN_NORM_DB, L.MEL_OUT_NORM_DB)
+        return self._ret(self._transpose(out), linear_spec)
+
+    def _griffin_lim(self, S, init_angles=None, return_sc=False):
+        """utils/audio.py:182-189; magnitude [num_freq, T] -> waveform"""
+        tt, lay = self._dt_in(S)
+        ang = self._host_angles(tuple(tt.shape[::-1]), init_angles)
+        out = self.griffin_lim_batch(tt, lay, L.SPEC_MAGNITUDE, init_angles=ang, return_sc=return_sc)
+        if return_sc:
+            return self._ret(out[0][:lay.wav_len[0]], S), self._ret(out[1][:, 0], S)
+        return self._ret(out[:lay.wav_len[0]], S)
+
+    def _stft(self, y):
+        """utils/audio.py:191-197; [L] -> complex64 [num_freq, T]"""
+        t, lay = self._wav_in(y)
+        torch = _torch()
+        D = self.stft_batch(t, lay)                                   # [T, F, 2]
+        re = self._transpose(D[..., 0].contiguous())
+        im = self._transpose(D[..., 1].contiguous())
+        out = torch.complex(re, im)
+        return out if self._is_tensor(y) else out.cpu().numpy()
+
+    def _istft(self, y):
+        """utils/audio.py:199-201; complex [num_freq, T] -> waveform [hop*(T-1)]"""
+        torch = _torch()
+        if self._is_tensor(y):
+            re, im = self._to_dev(y.real), self._to_dev(y.imag)
+        else:
+            y_np = np.asarray(y)
+            re, im = self._to_dev(np.ascontiguousarray(y_np.real)), self._to_dev(np.ascontiguousarray(y_np.imag))
+        D = torch.stack((self._transpose(re), self._transpose(im)), dim=-1).contiguous()   # [T, F, 2]
+        lay = self.layout(n_frames=[D.shape[0]])
+        out = self.istft_batch(D, lay)
+        return self._ret(out[:lay.wav_len[0]], y)
+
+    # ------------------------------------------------------------------------------------------ host helpers
+    # (file I/O and O(L) scalar post-processing: outside the kernel scope, kept for drop-in completeness)
+    def find_endpoint(self, wav, threshold_db=-40, min_silence_sec=0.8):
+        """utils/audio.py:203-210"""
+        window_length = int(self.sample_rate * min_silence_sec)
+        hop_length = int(window_length / 4)
+        threshold = np.power(10.0, threshold_db * 0.05)
+        for x in range(hop_length, len(wav) - window_length, hop_length):
+            if np.max(wav[x:x + window_length]) < threshold:
+                return x + hop_length
+        return len(wav)
+
+    def trim_silence(self, wav):
+        """utils/audio.py:212-217: 0.1 s margin, then librosa.effects.trim(top_db=40, frame_length=1024,
+        hop_length=256) restated (centred RMS frames, reference = max RMS)."""
+        margin = int(self.sample_rate * 0.1)
+        wav = np.asarray(wav)[margin:-margin]
+        frame_length, hop = 1024, 256
+        ypad = np.pad(wav, frame_length // 2, mode="reflect")
+        n = 1 + (len(ypad) - frame_length) // hop
+        idx = np.arange(frame_length)[None, :] + hop * np.arange(n)[:, None]
+        mse = np.mean(ypad[idx] ** 2, axis=1)
+        db = 10.0 * np.log10(np.maximum(1e-10, mse)) - 10.0 * np.log10(np.maximum(1e-10, mse.max()))
+        nz = np.flatnonzero(db > -40)
+        if nz.size == 0:
+            return wav[0:0]
+        start, end = int(nz[0] * hop), min(len(wav), int((nz[-1] + 1) * hop))
+        return wav[start:end]
+
+    @staticmethod
+    def mulaw_encode(wav, qc):
+        """utils/audio.py:219-226"""
+        mu = 2 ** qc - 1
+        signal = np.sign(wav) * np.log(1 + mu * np.abs(wav)) / np.log(1. + mu)
+        signal = (signal + 1) / 2 * mu + 0.5
+        return np.floor(signal,)
+
+    @staticmethod
+    def mulaw_decode(wav, qc):
+        """utils/audio.py:228-233"""
+        mu = 2 ** qc - 1
+        x = np.sign(wav) / mu * ((1 + mu) ** np.abs(wav) - 1)
+        return x
+
+    def load_wav(self, filename, sr=None):
+        """utils/audio.py:235-246 (soundfile is optional here; PCM wav files are read with scipy)."""
+        try:
+            import soundfile as sf
+            x, file_sr = sf.read(filename)
+        except ImportError:
+            from scipy.io import wavfile
+            file_sr, data = wavfile.read(filename)
+            if data.dtype.kind == "i":
+                x = data.astype(np.float64) / float(2 ** (8 * data.dtype.itemsize - 1))
+            elif data.dtype.kind == "u":
+                x = (data.astype(np.float64) - 128.0) / 128.0
+            else:
+                x = data.astype(np.float64)
+        if sr is not None and sr != file_sr:
+            raise RuntimeError("resampling on load (librosa.load) is not part of this package: %s has sr %s" % (filename, file_sr))
+        if self.do_trim_silence:
+            try:
+                x = self.trim_silence(x)
+            except ValueError:
+                print(f' [!] File cannot be trimmed for silence - {filename}')
+        assert self.sample_rate == file_sr, "%s vs %s" % (self.sample_rate, file_sr)
+        return x
+
+    def encode_16bits(self, x):
+        return np.clip(x * 2**15, -2**15, 2**15 - 1).astype(np.int16)
+
+    def quantize(self, x, bits):
+        return (x + 1.) * (2**bits - 1) / 2
+
+    def dequantize(self, x, bits):
+        return 2 * x / (2**bits - 1) - 1

@@ -1,0 +1,482 @@
+// Frame kernels: one warp owns one STFT frame (n_fft 2048 as a packed complex 1024-point FFT = 32 x 32,
+// one shared-memory exchange per transform), one CTA streams over runs of consecutive frames of an utterance.
+//
+//   MODE_GL_ITER   y -> [window, FFT] -> |S| e^{j angle X} -> [iFFT, window, overlap-add, / wss] -> y'
+//                  (utils/audio.py:186-188, one Griffin-Lim iteration in ONE HBM round trip)
+//   MODE_SYNTH     spectrum (|S| e^{j theta0} or complex) -> iFFT -> overlap-add        (utils/audio.py:183-185, 199-201)
+//   MODE_ANALYSIS  wav -> [pre-emphasis, reflect pad, window, FFT] -> complex or normalised dB linear/mel
+//                  (utils/audio.py:138-152, 191-197)
+//
+// The window (win taps, centred in n_fft) is shorter than the transform, and a circular shift of the frame is a
+// pure phase ramp that the per-bin projection S*X/|X| and the inverse transform undo exactly, so every frame is
+// processed in "shifted" coordinates: tap m of the window is sample m of the transform, only ceil(win/2) packed
+// inputs are non-zero and only the first win outputs of the inverse are needed.  (MODE_ANALYSIS with complex
+// output and MODE_SYNTH with complex input apply the ramp explicitly.)
+#pragma once
+#include "common.cuh"
+#include "fft32.cuh"
+
+namespace ttsa {
+
+enum { MODE_GL_ITER = 0, MODE_SYNTH = 1, MODE_ANALYSIS = 2 };
+enum { SRC_MAG = 0, SRC_NORM_DB = 1, SRC_COMPLEX = 2 };   // GL_ITER / SYNTH input kind
+enum { OUT_COMPLEX = 0, OUT_FEATURES = 1 };               // ANALYSIS output kind
+
+struct FrameArgs {
+  const float* spec;      // [sum_T, F]      GL_ITER / SYNTH (mag or normalised dB)
+  const float* angles;    // [sum_T, F]      SYNTH: initial phases in radians, or nullptr -> counter RNG
+  const float* cplx_in;   // [sum_T, F, 2]   SYNTH with SRC_COMPLEX
+  const float* wav_in;    // packed wav      GL_ITER (previous y) / ANALYSIS
+  float* wav_out;         // packed wav      GL_ITER / SYNTH
+  float* cplx_out;        // [sum_T, F, 2]   ANALYSIS OUT_COMPLEX
+  float* lin_out;         // [sum_T, F]      ANALYSIS OUT_FEATURES (nullable)
+  float* mel_out;         // [sum_T, mels]   ANALYSIS OUT_FEATURES (nullable)
+  float* sc_acc;          // [B, 2]          GL_ITER with SC: (sum (|X|-S)^2, sum S^2)
+  unsigned long long seed;
+  int preemph;            // ANALYSIS: apply y[n] - p*y[n-1] while staging
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// counter-based RNG (Philox4x32-10) for the initial phases when none are injected
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigned long long ctr) {
+  unsigned int c0 = (unsigned int)ctr, c1 = (unsigned int)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+  unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return (float)(c0 >> 8) * (1.0f / 16777216.0f);   // [0, 1)
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-warp transform passes
+// ---------------------------------------------------------------------------------------------------------
+// v[n2] = z[lane + 32 n2]  ->  v[k1] = Z[32 k1 + lane]       (forward, e^{-j})
+template <int NZ>
+__device__ __forceinline__ void fwd_passes(float2 (&v)[32], float2* buf, const float2* tw, int lane) {
+  fft32<false, NZ>(v);                                   // over n2 -> k2
+#pragma unroll
+  for (int k2 = 1; k2 < 32; ++k2) {                      // W_1024^(lane * k2)
+    const float2 w = tw[k2 * 32 + lane];
+    const float x = v[k2].x * w.x - v[k2].y * w.y;
+    v[k2].y = v[k2].x * w.y + v[k2].y * w.x;
+    v[k2].x = x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k2 = 0; k2 < 32; ++k2) buf[k2 * kRowStride + lane] = v[k2];
+  __syncwarp();
+#pragma unroll
+  for (int n1 = 0; n1 < 32; n1 += 2) {
+    const float4 q = *reinterpret_cast<const float4*>(&buf[lane * kRowStride + n1]);
+    v[n1] = make_float2(q.x, q.y);
+    v[n1 + 1] = make_float2(q.z, q.w);
+  }
+  fft32<false, 32>(v);                                   // over n1 -> k1
+}
+
+// v[k1] = Z'[32 k1 + lane]  ->  v[n2] = z'[lane + 32 n2]      (inverse, e^{+j}, unnormalised)
+__device__ __forceinline__ void inv_passes(float2 (&v)[32], float2* buf, const float2* tw, int lane) {
+  fft32<true, 32>(v);                                    // over k1 -> n1
+#pragma unroll
+  for (int n1 = 1; n1 < 32; ++n1) {                      // conj(W_1024^(n1 * lane))
+    const float2 w = tw[n1 * 32 + lane];
+    const float x = v[n1].x * w.x + v[n1].y * w.y;
+    v[n1].y = v[n1].y * w.x - v[n1].x * w.y;
+    v[n1].x = x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int n1 = 0; n1 < 32; ++n1) buf[n1 * kRowStride + lane] = v[n1];
+  __syncwarp();
+#pragma unroll
+  for (int k2 = 0; k2 < 32; k2 += 2) {
+    const float4 q = *reinterpret_cast<const float4*>(&buf[lane * kRowStride + k2]);
+    v[k2] = make_float2(q.x, q.y);
+    v[k2 + 1] = make_float2(q.z, q.w);
+  }
+  fft32<true, 32>(v);                                    // over k2 -> n2 (outputs >= NZ are dead code)
+}
+
+// magnitude of one spectrogram value
+template <int SRC>
+__device__ __forceinline__ float spec_to_mag(float x, const Geo& g) {
+  if constexpr (SRC == SRC_NORM_DB) {
+    x = fminf(fmaxf(x, g.s_lo), g.s_hi);
+    return exp2f(fmaf(g.s_c1, x, g.s_c0));
+  } else {
+    return fabsf(x);
+  }
+}
+
+__device__ __forceinline__ float amp_to_norm_db(float a, const Geo& g) {
+  const float v = fmaf(g.n_a, log2f(fmaxf(g.min_amp, a)), g.n_b);
+  return fminf(fmaxf(v, g.n_lo), g.n_hi);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE, int SRC, int NZ, bool SC>
+__global__ void __launch_bounds__(kThreads, 2)
+frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr float kInvN = 1.0f / (float)kNfft;
+
+  float2* const buf = reinterpret_cast<float2*>(smem + warp * kBufFloats);
+  float* const plane0 = smem + g.sm_plane0;
+  float* const plane1 = smem + g.sm_plane1;
+  float* const wE = smem + g.sm_wE;
+  float* const wO = smem + g.sm_wO;
+  float* const pw = smem + g.sm_pw;
+  float2* const tw = reinterpret_cast<float2*>(smem + g.sm_tw);
+  float2* const gt = reinterpret_cast<float2*>(smem + g.sm_g);
+
+  // plan tables -> shared memory (once per persistent CTA)
+  for (int i = tid; i < 1024; i += kThreads) tw[i] = tb.tw[i];
+  for (int i = tid; i < 512; i += kThreads) gt[i] = tb.g[i];
+  for (int i = tid; i < g.wlen; i += kThreads) { wE[i] = tb.wE[i]; wO[i] = tb.wO[i]; }
+  if constexpr (MODE != MODE_ANALYSIS)
+    for (int i = tid; i < g.hop; i += kThreads) pw[i] = tb.pw[i];
+
+  // contiguous tile range of this CTA over the flattened (utterance, tile) list
+  const long long tile_lo = (long long)blockIdx.x * bd.total_tiles / gridDim.x;
+  const long long tile_hi = (long long)(blockIdx.x + 1) * bd.total_tiles / gridDim.x;
+  int u = 0;
+  {
+    int lo = 0, hi = bd.B;   // largest u with tile_off[u] <= tile_lo
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (bd.tile_off[mid] <= tile_lo) lo = mid; else hi = mid;
+    }
+    u = lo;
+  }
+
+  long long tile = tile_lo;
+  while (tile < tile_hi) {
+    while (u + 1 < bd.B && tile >= bd.tile_off[u + 1]) ++u;
+    const int T = bd.T[u];
+    const int toff = bd.tile_off[u];
+    const int ja = (int)(tile - toff);
+    const long long seg_end = tile_hi < (long long)bd.tile_off[u + 1] ? tile_hi : (long long)bd.tile_off[u + 1];
+    const int jb = (int)(seg_end - toff);
+    tile = seg_end;
+    const int L = bd.wav_len[u];                 // signal length (GL / SYNTH: hop*(T-1))
+    if (MODE != MODE_ANALYSIS && L <= 0) continue;
+    const long long frow0 = bd.frame_off[u];
+    const long long woff = bd.wav_off[u];
+
+    // frames of earlier tiles still overlap this segment's first owned sample: recompute them (no output)
+    const bool warm = (MODE != MODE_ANALYSIS) && ja > 0 && g.nwarm > 0;
+    const int first_needed = warm ? ja * kNF - g.nwarm : 0;
+    bool has_carry = false;
+    int cb = 0;
+    float sc_num = 0.0f, sc_den = 0.0f;
+
+    for (int jt = warm ? ja - 1 : ja; jt < jb; ++jt) {
+      const int t0 = jt * kNF;
+      const int i0 = t0 * g.hop - g.off0;        // sample index of span position 0
+      const bool write_out = jt >= ja;
+
+      __syncthreads();                           // previous tile's overlap-add has consumed slots and planes
+      if constexpr (MODE != MODE_SYNTH) {
+        // stage the contiguous input span, de-interleaved by parity (conflict-free re/im frame loads)
+        const float* __restrict__ src = a.wav_in + woff;
+        for (int s = tid; s < g.span_len; s += kThreads) {
+          const int j = reflect_index(i0 + s, L);
+          float val = __ldg(src + j);
+          if (MODE == MODE_ANALYSIS && a.preemph) {
+            const float prev = j > 0 ? __ldg(src + j - 1) : 0.0f;
+            val = fmaf(-g.preemph, prev, val);
+          }
+          ((s & 1) ? plane1 : plane0)[s >> 1] = val;
+        }
+        __syncthreads();
+      }
+
+      const int t = t0 + warp;
+      if (t < T && t >= first_needed) {
+        const long long row = frow0 + t;
+        const bool own = t >= ja * kNF;            // warm-up frames are copies of another segment's frames
+        float2 v[32];
+        // ------------------------------------------------------------------ forward half
+        if constexpr (MODE != MODE_SYNTH) {
+          const int o = warp * g.hop;
+          const float* re_p = (o & 1) ? plane1 + ((o - 1) >> 1) : plane0 + (o >> 1);
+          const float* im_p = (o & 1) ? plane0 + ((o + 1) >> 1) : plane1 + (o >> 1);
+#pragma unroll
+          for (int n2 = 0; n2 < 32; ++n2) {
+            if (n2 < NZ) {
+              const int q = lane + 32 * n2;
+              const bool in = q < g.half;
+              v[n2].x = in ? re_p[q] * wE[q] : 0.0f;
+              v[n2].y = in ? im_p[q] * wO[q] : 0.0f;
+            } else {
+              v[n2] = make_float2(0.0f, 0.0f);
+            }
+          }
+          fwd_passes<NZ>(v, buf, tw, lane);
+        }
+
+        // ------------------------------------------------------------------ per-bin step on conjugate pairs
+        // lane holds Z[32 k1 + lane]; bin k pairs with 1024 - k, held by lane (32 - lane) & 31.  Each lane
+        // processes the 16 pairs whose first member is its own register k1 < 16.
+        const int partner = (32 - lane) & 31;
+        const bool l0 = lane == 0;
+        float2 r[16];
+        if constexpr (MODE != MODE_SYNTH) {
+#pragma unroll
+          for (int k1 = 0; k1 < 16; ++k1) {
+            const float2 sv = l0 ? v[(32 - k1) & 31] : v[31 - k1];
+            r[k1].x = __shfl_sync(0xffffffffu, sv.x, partner);
+            r[k1].y = __shfl_sync(0xffffffffu, sv.y, partner);
+          }
+        }
+
+        if constexpr (MODE == MODE_ANALYSIS) {
+          // X[k] = (E2 + G_k D2)/2, X[1024-k] = conj(E2 - G_k D2)/2 ; undo the circular shift for complex output
+          float* magbuf = reinterpret_cast<float*>(buf);
+          if constexpr (SRC == OUT_FEATURES) __syncwarp();
+#pragma unroll
+          for (int k1 = 0; k1 < 16; ++k1) {
+            const int k = 32 * k1 + lane, kp = 1024 - k;
+            const float2 A = v[k1], B = r[k1];
+            const float2 E2 = make_float2(A.x + B.x, A.y - B.y);
+            const float2 D2 = make_float2(A.x - B.x, A.y + B.y);
+            const float2 G = gt[k];
+            const float2 Tt = make_float2(G.x * D2.x - G.y * D2.y, G.x * D2.y + G.y * D2.x);
+            float2 Xk = make_float2(0.5f * (E2.x + Tt.x), 0.5f * (E2.y + Tt.y));
+            float2 Xp = make_float2(0.5f * (E2.x - Tt.x), -0.5f * (E2.y - Tt.y));
+            if (l0 && k1 == 0) { Xk.y = 0.0f; Xp.y = 0.0f; }
+            if constexpr (SRC == OUT_COMPLEX) {
+              // frame tap m sits at transform sample lpad + m: X_true[k] = X[k] * exp(-j 2 pi k lpad / n_fft)
+              const int lpad = (kNfft - g.win) >> 1;
+              float sn, cs;
+              sincospif(-(float)((k * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
+              float2* out = reinterpret_cast<float2*>(a.cplx_out) + row * kF;
+              out[k] = make_float2(Xk.x * cs - Xk.y * sn, Xk.x * sn + Xk.y * cs);
+              sincospif(-(float)((kp * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
+              out[kp] = make_float2(Xp.x * cs - Xp.y * sn, Xp.x * sn + Xp.y * cs);
+            } else {
+              magbuf[k] = sqrtf(Xk.x * Xk.x + Xk.y * Xk.y);
+              magbuf[kp] = sqrtf(Xp.x * Xp.x + Xp.y * Xp.y);
+            }
+          }
+          if (l0) {   // k = 512: X = conj(Z[512])
+            const float2 Zc = v[16];
+            if constexpr (SRC == OUT_COMPLEX) {
+              const int lpad = (kNfft - g.win) >> 1;
+              float sn, cs;
+              sincospif(-(float)((512 * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
+              float2* out = reinterpret_cast<float2*>(a.cplx_out) + row * kF;
+              out[512] = make_float2(Zc.x * cs + Zc.y * sn, Zc.x * sn - Zc.y * cs);
+            } else {
+              magbuf[512] = sqrtf(Zc.x * Zc.x + Zc.y * Zc.y);
+            }
+          }
+          if constexpr (SRC == OUT_FEATURES) {
+            __syncwarp();
+            if (a.lin_out != nullptr) {
+              float* out = a.lin_out + row * kF;
+              for (int k = lane; k < kF; k += 32) out[k] = amp_to_norm_db(magbuf[k], g);
+            }
+            if (a.mel_out != nullptr) {
+              float* out = a.mel_out + row * g.num_mels;
+              for (int m = lane; m < g.num_mels; m += 32) {
+                const int lo = tb.mel_lo[m], cnt = tb.mel_cnt[m];
+                const float* mv = tb.mel_val + m * tb.mel_ld;
+                float acc = 0.0f;
+                for (int c = 0; c < cnt; ++c) acc = fmaf(__ldg(mv + c), magbuf[lo + c], acc);
+                out[m] = amp_to_norm_db(acc, g);
+              }
+            }
+            __syncwarp();
+          }
+        } else {
+          // ---------------------------------------------------------------- GL_ITER / SYNTH: build Y, then Z'
+          float2 snd[16];
+          float2 z512 = make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int k1 = 0; k1 < 16; ++k1) {
+            const int k = 32 * k1 + lane, kp = 1024 - k;
+            float2 Yk, Yp;
+            if constexpr (MODE == MODE_GL_ITER) {
+              const float Sk = spec_to_mag<SRC>(__ldg(a.spec + row * kF + k), g);
+              const float Sp = spec_to_mag<SRC>(__ldg(a.spec + row * kF + kp), g);
+              const float2 A = v[k1], B = r[k1];
+              const float2 E2 = make_float2(A.x + B.x, A.y - B.y);
+              const float2 D2 = make_float2(A.x - B.x, A.y + B.y);
+              const float2 G = gt[k];
+              const float2 Tt = make_float2(G.x * D2.x - G.y * D2.y, G.x * D2.y + G.y * D2.x);
+              const float2 Xk = make_float2(E2.x + Tt.x, E2.y + Tt.y);          // 2 X[k]
+              const float2 Xp = make_float2(E2.x - Tt.x, -(E2.y - Tt.y));       // 2 X[1024-k]
+              const float mk = Xk.x * Xk.x + Xk.y * Xk.y;
+              const float mp = Xp.x * Xp.x + Xp.y * Xp.y;
+              const float ik = rsqrtf(mk), ip = rsqrtf(mp);
+              const float fk = Sk * kInvN * ik, fp = Sp * kInvN * ip;
+              // np.angle(0) = 0  ->  Y = S
+              Yk = mk > 1e-37f ? make_float2(Xk.x * fk, Xk.y * fk) : make_float2(Sk * kInvN, 0.0f);
+              Yp = mp > 1e-37f ? make_float2(Xp.x * fp, Xp.y * fp) : make_float2(Sp * kInvN, 0.0f);
+              if (SC && own) {
+                const float dk = 0.5f * mk * ik - Sk, dp = 0.5f * mp * ip - Sp;
+                sc_num += (mk > 1e-37f ? dk * dk : Sk * Sk) + (mp > 1e-37f ? dp * dp : Sp * Sp);
+                sc_den += Sk * Sk + Sp * Sp;
+              }
+            } else if constexpr (SRC == SRC_COMPLEX) {
+              // shifted coordinates: Y'[k] = Y[k] * exp(+j 2 pi k lpad / n_fft)
+              const int lpad = (kNfft - g.win) >> 1;
+              const float2* in = reinterpret_cast<const float2*>(a.cplx_in) + row * kF;
+              const float2 ck = in[k], cp = in[kp];
+              float sn, cs;
+              sincospif((float)((k * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
+              Yk = make_float2((ck.x * cs - ck.y * sn) * kInvN, (ck.x * sn + ck.y * cs) * kInvN);
+              sincospif((float)((kp * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
+              Yp = make_float2((cp.x * cs - cp.y * sn) * kInvN, (cp.x * sn + cp.y * cs) * kInvN);
+            } else {
+              const float Sk = spec_to_mag<SRC>(__ldg(a.spec + row * kF + k), g) * kInvN;
+              const float Sp = spec_to_mag<SRC>(__ldg(a.spec + row * kF + kp), g) * kInvN;
+              float sk, ck, sp, cp;
+              if (a.angles != nullptr) {
+                sincosf(__ldg(a.angles + row * kF + k), &sk, &ck);
+                sincosf(__ldg(a.angles + row * kF + kp), &sp, &cp);
+              } else {
+                sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + k)), &sk, &ck);
+                sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + kp)), &sp, &cp);
+              }
+              Yk = make_float2(Sk * ck, Sk * sk);
+              Yp = make_float2(Sp * cp, Sp * sp);
+            }
+            if (MODE == MODE_SYNTH && l0 && k1 == 0) { Yk.y = 0.0f; Yp.y = 0.0f; }   // irfft ignores Im of DC / Nyquist
+            // Z'2[k] = P + Q, Z'2[1024-k] = conj(P - Q),  P = Y[k] + conj(Y[1024-k]),  Q = conj(G_k) (Y[k] - conj(Y[1024-k]))
+            const float2 G = gt[k];
+            const float2 P = make_float2(Yk.x + Yp.x, Yk.y - Yp.y);
+            const float2 D = make_float2(Yk.x - Yp.x, Yk.y + Yp.y);
+            const float2 Q = make_float2(G.x * D.x + G.y * D.y, G.x * D.y - G.y * D.x);
+            v[k1] = make_float2(P.x + Q.x, P.y + Q.y);
+            snd[k1] = make_float2(P.x - Q.x, -(P.y - Q.y));
+          }
+          if (l0) {   // k = 512 (self-paired): X = conj(Z[512]), Z'2 = 2 conj(Y)
+            float2 Y;
+            if constexpr (MODE == MODE_GL_ITER) {
+              const float S5 = spec_to_mag<SRC>(__ldg(a.spec + row * kF + 512), g);
+              const float2 X = make_float2(v[16].x, -v[16].y);
+              const float m = X.x * X.x + X.y * X.y;
+              const float im = rsqrtf(m);
+              const float f = S5 * kInvN * im;
+              Y = m > 1e-37f ? make_float2(X.x * f, X.y * f) : make_float2(S5 * kInvN, 0.0f);
+              if (SC && own) {
+                const float d = m * im - S5;         // |X| = |Z[512]| (no factor 2 here)
+                sc_num += m > 1e-37f ? d * d : S5 * S5;
+                sc_den += S5 * S5;
+              }
+            } else if constexpr (SRC == SRC_COMPLEX) {
+              const int lpad = (kNfft - g.win) >> 1;
+              const float2 c5 = (reinterpret_cast<const float2*>(a.cplx_in) + row * kF)[512];
+              float sn, cs;
+              sincospif((float)((512 * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
+              Y = make_float2((c5.x * cs - c5.y * sn) * kInvN, (c5.x * sn + c5.y * cs) * kInvN);
+            } else {
+              const float S5 = spec_to_mag<SRC>(__ldg(a.spec + row * kF + 512), g) * kInvN;
+              float s5, c5;
+              if (a.angles != nullptr) sincosf(__ldg(a.angles + row * kF + 512), &s5, &c5);
+              else sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + 512)), &s5, &c5);
+              Y = make_float2(S5 * c5, S5 * s5);
+            }
+            z512 = make_float2(2.0f * Y.x, -2.0f * Y.y);
+          }
+          // hand the partner its half of each pair
+#pragma unroll
+          for (int k1 = 0; k1 < 16; ++k1) {
+            r[k1].x = __shfl_sync(0xffffffffu, snd[k1].x, partner);
+            r[k1].y = __shfl_sync(0xffffffffu, snd[k1].y, partner);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 from_other = r[15 - i];                             // own register 31 - k1
+            const float2 from_self = i == 0 ? z512 : r[16 - i];              // lane 0: own register 32 - k1
+            v[16 + i] = l0 ? from_self : from_other;
+          }
+
+          // ---------------------------------------------------------------- inverse half
+          inv_passes(v, buf, tw, lane);
+          __syncwarp();                       // all lanes done reading the exchange buffer: it becomes the slot
+          float* slot = reinterpret_cast<float*>(buf);
+#pragma unroll
+          for (int n2 = 0; n2 < 32; ++n2) {
+            if (n2 < NZ) {
+              const int q = lane + 32 * n2;
+              if (q < g.half)
+                *reinterpret_cast<float2*>(slot + 2 * q) = make_float2(v[n2].x * wE[q], v[n2].y * wO[q]);
+            }
+          }
+        }
+      }
+
+      if constexpr (MODE != MODE_ANALYSIS) {
+        __syncthreads();
+        // -------------------------------------------------------------------- overlap-add + 1/wss + store
+        const int fv_lo = first_needed > t0 ? first_needed - t0 : 0;
+        const int fv_hi = (T - t0) < kNF ? (T - t0) : kNF;
+        const float* carry_old = smem + (cb ? g.sm_carry1 : g.sm_carry0);
+        float* carry_new = smem + (cb ? g.sm_carry0 : g.sm_carry1);
+        float* __restrict__ dst = a.wav_out + woff;
+        const int out_len = kNF * g.hop;
+        for (int s = tid; s < g.span_len; s += kThreads) {
+          const int q = (int)(((float)s + 0.5f) * g.inv_hop);
+          const int rr = s - q * g.hop;
+          float sum = (has_carry && s < g.carry_len) ? carry_old[s] : 0.0f;
+          for (int d = 0, m = rr; m < g.win; ++d, m += g.hop) {
+            const int f = q - d;
+            if (f >= fv_lo && f < fv_hi) sum += smem[f * kBufFloats + m];
+          }
+          if (s < out_len) {
+            const int i = i0 + s;
+            if (write_out && i >= 0 && i < L) {
+              const int dmax = (g.win - 1 - rr) / g.hop;
+              const int tlo = t0 + q - dmax, thi = t0 + q;
+              float inv;
+              if (tlo >= 0 && thi <= T - 1) {
+                inv = pw[rr];
+              } else {
+                float ws = 0.0f;
+                for (int d = 0, m = rr; m < g.win; ++d, m += g.hop) {
+                  const int tt = t0 + q - d;
+                  if (tt >= 0 && tt < T) {
+                    const float wv = (m & 1) ? wO[m >> 1] : wE[m >> 1];
+                    ws = fmaf(wv, wv, ws);
+                  }
+                }
+                inv = ws > 1.17549435e-38f ? 1.0f / ws : 1.0f;   // librosa: divide only where wss > tiny
+              }
+              dst[i] = sum * inv;
+            }
+          } else {
+            carry_new[s - out_len] = sum;
+          }
+        }
+        has_carry = true;
+        cb ^= 1;
+      }
+    }  // tiles of the segment
+
+    if constexpr (MODE == MODE_GL_ITER && SC) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sc_num += __shfl_xor_sync(0xffffffffu, sc_num, o);
+        sc_den += __shfl_xor_sync(0xffffffffu, sc_den, o);
+      }
+      if (lane == 0) {
+        atomicAdd(a.sc_acc + 2 * u, sc_num);
+        atomicAdd(a.sc_acc + 2 * u + 1, sc_den);
+      }
+    }
+  }  // segments
+}
+
+}  // namespace ttsa

@@ -1,0 +1,619 @@
+// C ABI of libttsa_b200.so (see include/ttsa.h).  Host logic: plan tables, batch layout, kernel orchestration.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/ttsa.h"
+#include "aux_kernels.cuh"
+#include "frame_launch.cuh"
+#include "host_tables.hpp"
+
+using namespace ttsa;
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+std::atomic<unsigned long long> ttsa::g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(TTSA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));    \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------------------
+struct ttsa_plan {
+  ttsa_config cfg;
+  int device = -1;          // -1: host-only plan (tables on the host; no work calls)
+  int num_sms = 0;
+  Geo geo;
+  Tables tb;
+  MelParams mel;
+  PwParams pw;
+  std::vector<double> h_mel;       // [num_mels][F]
+  std::vector<double> h_inv_mel;   // [F][num_mels]
+  int nz = 32;                     // compile-time zero-pruning class of the frame kernels (20 or 32)
+  int ctas_per_sm = 1;
+  // device allocations
+  void* d_block = nullptr;         // one allocation holding every table
+  const float* d_pinvT = nullptr;  // [num_mels][ldp]
+  int ldp = 0;
+};
+
+struct ttsa_batch {
+  int device = -1;
+  int B = 0;
+  int hop = 0;
+  std::vector<int> T, wav_len, tile_off, chunk_off;
+  std::vector<long long> frame_off, wav_off;
+  long long total_frames = 0, total_samples = 0;
+  int max_chunks = 0;
+  void* d_block = nullptr;
+  BatchDev dev;
+  const int* d_chunk_off = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ttsa_version(void) { return TTSA_VERSION; }
+extern "C" const char* ttsa_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint64_t ttsa_launch_count(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------------------
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+static int build_geo(const ttsa_config& c, Geo& g) {
+  std::memset(&g, 0, sizeof(g));
+  g.hop = c.hop_length;
+  g.win = c.win_length;
+  const int lpad = (kNfft - c.win_length) / 2;
+  g.off0 = kNfft / 2 - lpad;
+  g.half = (c.win_length + 1) / 2;
+  g.wlen = round_up(g.half, 32);
+  g.carry_len = c.win_length - c.hop_length;
+  g.span_len = (kNF - 1) * c.hop_length + c.win_length;
+  g.nwarm = (c.win_length - 1) / c.hop_length;
+  g.num_mels = c.num_mels;
+  g.inv_hop = 1.0f / (float)c.hop_length;
+  g.preemph = (float)c.preemphasis;
+  // shared memory layout
+  int off = kNF * kBufFloats;
+  const int plane_len = (g.span_len + 1) / 2 + 1;
+  g.sm_plane0 = off;
+  off += round_up(plane_len, 32) + 16;          // plane1 starts 16 banks away from plane0
+  g.sm_plane1 = off;
+  off += round_up(plane_len, 32);
+  g.sm_carry0 = off; off += round_up(g.carry_len + 1, 4);
+  g.sm_carry1 = off; off += round_up(g.carry_len + 1, 4);
+  g.sm_wE = off; off += g.wlen;
+  g.sm_wO = off; off += g.wlen;
+  g.sm_pw = off; off += round_up(g.hop, 4);
+  g.sm_tw = off; off += 2048;
+  g.sm_g = off; off += 1024;
+  g.sm_total = off;
+
+  // value conversions (utils/audio.py:79-126)
+  const double LOG2_10 = std::log2(10.0);
+  const double mn = c.max_norm, mdb = c.min_level_db, ref = c.ref_level_db;
+  double da = 1.0, db0 = 0.0, lo = -INFINITY, hi = INFINITY;
+  if (c.signal_norm) {
+    if (c.symmetric_norm) { da = -mdb / (2.0 * mn); db0 = mdb / 2.0; if (c.clip_norm) { lo = -mn; hi = mn; } }
+    else                  { da = -mdb / mn;         db0 = mdb;       if (c.clip_norm) { lo = 0.0; hi = mn; } }
+  }
+  const double a_c1 = 0.05 * LOG2_10 * da, a_c0 = 0.05 * LOG2_10 * (db0 + ref);
+  g.s_c1 = (float)(c.power * a_c1);
+  g.s_c0 = (float)(c.power * a_c0);
+  g.s_lo = (float)lo;
+  g.s_hi = (float)hi;
+  const double cdb = 20.0 * std::log10(2.0);
+  double n_a = cdb, n_b = -ref, n_lo = -INFINITY, n_hi = INFINITY;
+  if (c.signal_norm) {
+    if (c.symmetric_norm) {
+      n_a = 2.0 * mn * cdb / -mdb; n_b = 2.0 * mn * (-ref - mdb) / -mdb - mn;
+      if (c.clip_norm) { n_lo = -mn; n_hi = mn; }
+    } else {
+      n_a = mn * cdb / -mdb; n_b = mn * (-ref - mdb) / -mdb;
+      if (c.clip_norm) { n_lo = 0.0; n_hi = mn; }
+    }
+  }
+  g.n_a = (float)n_a; g.n_b = (float)n_b; g.n_lo = (float)n_lo; g.n_hi = (float)n_hi;
+  g.min_amp = (float)std::pow(10.0, mdb / 20.0);
+  return 0;
+}
+
+extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** out) {
+  if (!cfg || !out) return fail(TTSA_ERR_BAD_ARG, "null argument");
+  *out = nullptr;
+  const ttsa_config& c = *cfg;
+  if (c.sample_rate <= 0 || c.num_mels <= 0 || c.num_freq < 2)
+    return fail(TTSA_ERR_BAD_CONFIG, "sample_rate, num_mels and num_freq must be positive");
+  if (c.n_fft != (c.num_freq - 1) * 2) return fail(TTSA_ERR_BAD_CONFIG, "n_fft must equal (num_freq - 1) * 2");
+  if (c.mel_fmax > 0 && c.mel_fmax > c.sample_rate / 2)   // assert at utils/audio.py:70-71 (integer sr // 2)
+    return fail(TTSA_ERR_BAD_CONFIG, "mel_fmax %.1f > sample_rate // 2 = %d", c.mel_fmax, c.sample_rate / 2);
+  if (c.n_fft != kNfft) return fail(TTSA_ERR_UNSUPPORTED, "num_freq %d: only num_freq 1025 (n_fft 2048) is built", c.num_freq);
+  if (c.hop_length < 2 || c.win_length < c.hop_length || c.win_length > kNfft)
+    return fail(TTSA_ERR_UNSUPPORTED, "need 2 <= hop_length <= win_length <= n_fft (hop %d, win %d)", c.hop_length, c.win_length);
+  if (c.win_length - c.hop_length > kNF * c.hop_length)
+    return fail(TTSA_ERR_UNSUPPORTED, "win_length %d > %d * hop_length %d", c.win_length, kNF + 1, c.hop_length);
+  if (c.num_mels > kMtlMaxK) return fail(TTSA_ERR_UNSUPPORTED, "num_mels %d > %d", c.num_mels, kMtlMaxK);
+  if (c.signal_norm && (c.max_norm <= 0 || c.min_level_db >= 0))
+    return fail(TTSA_ERR_BAD_CONFIG, "signal_norm needs max_norm > 0 and min_level_db < 0");
+
+  ttsa_plan* p = new ttsa_plan();
+  p->cfg = c;
+  p->device = device;
+  build_geo(c, p->geo);
+  p->nz = (p->geo.half <= 20 * 32) ? 20 : 32;
+  if ((size_t)p->geo.sm_total * 4 > 227 * 1024) {
+    delete p;
+    return fail(TTSA_ERR_UNSUPPORTED, "hop/win need %d bytes of shared memory per CTA", p->geo.sm_total * 4);
+  }
+
+  // ---- host tables (float64) ----
+  const double fmax = c.mel_fmax > 0 ? c.mel_fmax : 0.5 * c.sample_rate;
+  p->h_mel = ttsa_host::mel_basis(c.sample_rate, c.n_fft, c.num_mels, c.mel_fmin, fmax);
+  p->h_inv_mel = ttsa_host::pinv_wide(p->h_mel, c.num_mels, kF);
+
+  // elementwise parameter blocks
+  p->pw.signal_norm = c.signal_norm; p->pw.symmetric_norm = c.symmetric_norm; p->pw.clip_norm = c.clip_norm;
+  p->pw.min_level_db = (float)c.min_level_db; p->pw.max_norm = (float)c.max_norm; p->pw.min_amp = p->geo.min_amp;
+  p->pw.op = 0;
+  MelParams& mp = p->mel;
+  mp.a_c1 = (float)(p->geo.s_c1 / c.power); mp.a_c0 = (float)(p->geo.s_c0 / c.power);
+  {  // recompute without the power factor to avoid the division rounding (and power == 0)
+    Geo g1; ttsa_config c1 = c; c1.power = 1.0; build_geo(c1, g1);
+    mp.a_c1 = g1.s_c1; mp.a_c0 = g1.s_c0;
+  }
+  mp.a_lo = p->geo.s_lo; mp.a_hi = p->geo.s_hi;
+  mp.n_a = p->geo.n_a; mp.n_b = p->geo.n_b; mp.n_lo = p->geo.n_lo; mp.n_hi = p->geo.n_hi; mp.min_amp = p->geo.min_amp;
+  mp.power = (float)c.power; mp.num_mels = c.num_mels; mp.rows = 0;
+
+  if (device < 0) { *out = p; return TTSA_OK; }
+
+  // ---- device tables ----
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
+    delete p;
+    return fail(TTSA_ERR_NO_DEVICE, "CUDA device %d not available (%d devices)", device, ndev);
+  }
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    delete p;
+    return fail(TTSA_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  }
+  p->num_sms = prop.multiProcessorCount;
+
+  const std::vector<double> w = ttsa_host::hann_periodic(c.win_length);
+  std::vector<float> h_tw(2048), h_g(1024), h_wE(1024, 0.f), h_wO(1024, 0.f), h_pw(round_up(c.hop_length, 4), 1.f);
+  for (int a = 0; a < 32; ++a)
+    for (int b = 0; b < 32; ++b) {
+      const double ang = 2.0 * ttsa_host::kPi * ((a * b) % 1024) / 1024.0;
+      h_tw[2 * (a * 32 + b)] = (float)std::cos(ang);
+      h_tw[2 * (a * 32 + b) + 1] = (float)-std::sin(ang);
+    }
+  for (int k = 0; k < 512; ++k) {
+    const double ang = ttsa_host::kPi * k / 1024.0;
+    h_g[2 * k] = (float)-std::sin(ang);
+    h_g[2 * k + 1] = (float)-std::cos(ang);
+  }
+  for (int m = 0; m < c.win_length; ++m) ((m & 1) ? h_wO : h_wE)[m >> 1] = (float)w[m];
+  for (int r = 0; r < c.hop_length; ++r) {
+    double acc = 0.0;
+    for (int m = r; m < c.win_length; m += c.hop_length) { const double wf = (double)(float)w[m]; acc += wf * wf; }
+    h_pw[r] = (float)(1.0 / acc);
+  }
+  // banded mel basis
+  std::vector<int> h_lo(c.num_mels, 0), h_cnt(c.num_mels, 0);
+  int ld = 1;
+  for (int m = 0; m < c.num_mels; ++m) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < kF; ++k)
+      if (p->h_mel[(size_t)m * kF + k] != 0.0) { if (lo < 0) lo = k; hi = k; }
+    if (lo >= 0) { h_lo[m] = lo; h_cnt[m] = hi - lo + 1; ld = std::max(ld, hi - lo + 1); }
+  }
+  ld = round_up(ld, 4);
+  std::vector<float> h_val((size_t)c.num_mels * ld, 0.f);
+  for (int m = 0; m < c.num_mels; ++m)
+    for (int cidx = 0; cidx < h_cnt[m]; ++cidx) h_val[(size_t)m * ld + cidx] = (float)p->h_mel[(size_t)m * kF + h_lo[m] + cidx];
+  p->ldp = round_up(kF, 4);
+  std::vector<float> h_pinvT((size_t)c.num_mels * p->ldp, 0.f);
+  for (int k = 0; k < kF; ++k)
+    for (int m = 0; m < c.num_mels; ++m) h_pinvT[(size_t)m * p->ldp + k] = (float)p->h_inv_mel[(size_t)k * c.num_mels + m];
+
+  // one device block
+  struct Piece { const void* src; size_t bytes; size_t off; };
+  std::vector<Piece> pieces = {
+      {h_tw.data(), h_tw.size() * 4, 0}, {h_g.data(), h_g.size() * 4, 0}, {h_wE.data(), h_wE.size() * 4, 0},
+      {h_wO.data(), h_wO.size() * 4, 0}, {h_pw.data(), h_pw.size() * 4, 0}, {h_lo.data(), h_lo.size() * 4, 0},
+      {h_cnt.data(), h_cnt.size() * 4, 0}, {h_val.data(), h_val.size() * 4, 0}, {h_pinvT.data(), h_pinvT.size() * 4, 0}};
+  size_t total = 0;
+  for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
+  if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
+    delete p;
+    return fail(TTSA_ERR_CUDA, "cudaMalloc(%zu) for plan tables failed", total);
+  }
+  for (auto& pc : pieces) {
+    cudaError_t e = cudaMemcpy((char*)p->d_block + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
+  }
+  char* base = (char*)p->d_block;
+  p->tb.tw = (const float2*)(base + pieces[0].off);
+  p->tb.g = (const float2*)(base + pieces[1].off);
+  p->tb.wE = (const float*)(base + pieces[2].off);
+  p->tb.wO = (const float*)(base + pieces[3].off);
+  p->tb.pw = (const float*)(base + pieces[4].off);
+  p->tb.mel_lo = (const int*)(base + pieces[5].off);
+  p->tb.mel_cnt = (const int*)(base + pieces[6].off);
+  p->tb.mel_val = (const float*)(base + pieces[7].off);
+  p->tb.mel_ld = ld;
+  p->d_pinvT = (const float*)(base + pieces[8].off);
+
+  // configure every kernel once (dynamic shared memory opt-in, occupancy), outside any stream capture
+  const size_t smem_bytes = (size_t)p->geo.sm_total * 4;
+  int occ = 0;
+  const char* err = configure_frame_kernels(smem_bytes, &occ);
+  if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
+  p->ctas_per_sm = occ < 1 ? 1 : occ;
+  cudaError_t e = cudaFuncSetAttribute(mel_to_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kMtlMaxK * (kMtlBins + kMtlRows) * 4);
+  if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "mel kernel configuration: %s", cudaGetErrorString(e)); }
+  *out = p;
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_plan_destroy(ttsa_plan* plan) {
+  if (!plan) return TTSA_OK;
+  if (plan->d_block) { DeviceGuard g(plan->device); cudaFree(plan->d_block); }
+  delete plan;
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_plan_mel_basis(const ttsa_plan* plan, double* host_out) {
+  if (!plan || !host_out) return fail(TTSA_ERR_BAD_ARG, "null argument");
+  std::memcpy(host_out, plan->h_mel.data(), plan->h_mel.size() * sizeof(double));
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_plan_inv_mel_basis(const ttsa_plan* plan, double* host_out) {
+  if (!plan || !host_out) return fail(TTSA_ERR_BAD_ARG, "null argument");
+  std::memcpy(host_out, plan->h_inv_mel.data(), plan->h_inv_mel.size() * sizeof(double));
+  return TTSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batch layout
+// ---------------------------------------------------------------------------------------------------------
+static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out) {
+  const int B = b->B;
+  b->device = plan->device;
+  b->hop = plan->cfg.hop_length;
+  b->frame_off.assign(B + 1, 0); b->wav_off.assign(B + 1, 0); b->tile_off.assign(B + 1, 0); b->chunk_off.assign(B + 1, 0);
+  b->max_chunks = 0;
+  for (int u = 0; u < B; ++u) {
+    b->frame_off[u + 1] = b->frame_off[u] + b->T[u];
+    b->wav_off[u + 1] = b->wav_off[u] + (b->wav_len[u] + 3) / 4 * 4;
+    const long long tiles = (long long)b->tile_off[u] + (b->T[u] + kNF - 1) / kNF;
+    if (tiles > std::numeric_limits<int>::max()) { delete b; return fail(TTSA_ERR_BAD_ARG, "batch too large"); }
+    b->tile_off[u + 1] = (int)tiles;
+    const int ch = (b->wav_len[u] + kDeChunk - 1) / kDeChunk;
+    b->chunk_off[u + 1] = b->chunk_off[u] + ch;
+    b->max_chunks = std::max(b->max_chunks, ch);
+  }
+  b->total_frames = b->frame_off[B];
+  b->total_samples = b->wav_off[B];
+  std::memset(&b->dev, 0, sizeof(b->dev));
+  b->dev.B = B;
+  b->dev.total_tiles = b->tile_off[B];
+  if (plan->device >= 0) {
+    DeviceGuard guard(plan->device);
+    const size_t n_i = (size_t)B * 2 + (size_t)(B + 1) * 2;     // T, wav_len, tile_off, chunk_off
+    const size_t bytes_i = (n_i * 4 + 15) / 16 * 16;
+    const size_t bytes_l = (size_t)(B + 1) * 2 * 8;
+    if (cudaMalloc(&b->d_block, bytes_i + bytes_l) != cudaSuccess) { delete b; return fail(TTSA_ERR_CUDA, "cudaMalloc for batch layout failed"); }
+    std::vector<char> h(bytes_i + bytes_l, 0);
+    long long* hl = (long long*)h.data();
+    std::memcpy(hl, b->frame_off.data(), (B + 1) * 8);
+    std::memcpy(hl + (B + 1), b->wav_off.data(), (B + 1) * 8);
+    int* hi = (int*)(h.data() + bytes_l);
+    std::memcpy(hi, b->T.data(), B * 4);
+    std::memcpy(hi + B, b->wav_len.data(), B * 4);
+    std::memcpy(hi + 2 * B, b->tile_off.data(), (B + 1) * 4);
+    std::memcpy(hi + 2 * B + (B + 1), b->chunk_off.data(), (B + 1) * 4);
+    cudaError_t e = cudaMemcpy(b->d_block, h.data(), h.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(b->d_block); delete b; return fail(TTSA_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e)); }
+    const long long* dl = (const long long*)b->d_block;
+    const int* di = (const int*)((char*)b->d_block + bytes_l);
+    b->dev.frame_off = dl;
+    b->dev.wav_off = dl + (B + 1);
+    b->dev.T = di;
+    b->dev.wav_len = di + B;
+    b->dev.tile_off = di + 2 * B;
+    b->d_chunk_off = di + 2 * B + (B + 1);
+  }
+  *out = b;
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_batch_from_frames(const ttsa_plan* plan, const int32_t* n_frames_host, int32_t n_utts, ttsa_batch** out) {
+  if (!plan || !n_frames_host || !out || n_utts <= 0) return fail(TTSA_ERR_BAD_ARG, "bad argument");
+  *out = nullptr;
+  ttsa_batch* b = new ttsa_batch();
+  b->B = n_utts;
+  b->T.resize(n_utts); b->wav_len.resize(n_utts);
+  for (int u = 0; u < n_utts; ++u) {
+    if (n_frames_host[u] < 0) { delete b; return fail(TTSA_ERR_BAD_ARG, "negative frame count at %d", u); }
+    b->T[u] = n_frames_host[u];
+    b->wav_len[u] = n_frames_host[u] > 0 ? plan->cfg.hop_length * (n_frames_host[u] - 1) : 0;
+  }
+  return batch_finish(plan, b, out);
+}
+
+extern "C" int ttsa_batch_from_wav_lengths(const ttsa_plan* plan, const int32_t* wav_len_host, int32_t n_utts, ttsa_batch** out) {
+  if (!plan || !wav_len_host || !out || n_utts <= 0) return fail(TTSA_ERR_BAD_ARG, "bad argument");
+  *out = nullptr;
+  ttsa_batch* b = new ttsa_batch();
+  b->B = n_utts;
+  b->T.resize(n_utts); b->wav_len.resize(n_utts);
+  for (int u = 0; u < n_utts; ++u) {
+    if (wav_len_host[u] < 1) { delete b; return fail(TTSA_ERR_BAD_ARG, "wav length at %d must be >= 1 (reflect padding)", u); }
+    b->wav_len[u] = wav_len_host[u];
+    b->T[u] = 1 + wav_len_host[u] / plan->cfg.hop_length;
+  }
+  return batch_finish(plan, b, out);
+}
+
+extern "C" int ttsa_batch_destroy(ttsa_batch* batch) {
+  if (!batch) return TTSA_OK;
+  if (batch->d_block) { DeviceGuard g(batch->device); cudaFree(batch->d_block); }
+  delete batch;
+  return TTSA_OK;
+}
+
+extern "C" int64_t ttsa_batch_total_frames(const ttsa_batch* b) { return b ? b->total_frames : -1; }
+extern "C" int64_t ttsa_batch_total_samples(const ttsa_batch* b) { return b ? b->total_samples : -1; }
+
+extern "C" int ttsa_batch_offsets(const ttsa_batch* b, int64_t* frame_off, int64_t* wav_off, int32_t* wav_len) {
+  if (!b) return fail(TTSA_ERR_BAD_ARG, "null batch");
+  for (int u = 0; u <= b->B; ++u) {
+    if (frame_off) frame_off[u] = b->frame_off[u];
+    if (wav_off) wav_off[u] = b->wav_off[u];
+    if (wav_len && u < b->B) wav_len[u] = b->wav_len[u];
+  }
+  return TTSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// work calls
+// ---------------------------------------------------------------------------------------------------------
+static int check_work(const ttsa_plan* plan, const ttsa_batch* batch) {
+  if (!plan || !batch) return fail(TTSA_ERR_BAD_ARG, "null plan or batch");
+  if (plan->device < 0) return fail(TTSA_ERR_NO_DEVICE, "host-only plan: no CUDA device bound; this library has no CPU path");
+  if (batch->device != plan->device) return fail(TTSA_ERR_BAD_ARG, "batch belongs to device %d, plan to %d", batch->device, plan->device);
+  if (batch->hop != plan->cfg.hop_length) return fail(TTSA_ERR_BAD_ARG, "batch was laid out for hop %d", batch->hop);
+  return TTSA_OK;
+}
+
+static int launch_frames(const ttsa_plan* plan, const ttsa_batch* batch, int mode, int src, bool sc,
+                         const FrameArgs& args, cudaStream_t st) {
+  if (batch->dev.total_tiles == 0) return TTSA_OK;
+  const int max_ctas = plan->ctas_per_sm * plan->num_sms;
+  const int grid = batch->dev.total_tiles < max_ctas ? batch->dev.total_tiles : max_ctas;
+  const char* err = launch_frame_kernel(mode, src, plan->nz, sc, grid, (size_t)plan->geo.sm_total * 4, st, plan->geo,
+                                        plan->tb, batch->dev, args);
+  if (err) return fail(TTSA_ERR_CUDA, "frame kernel launch (mode %d): %s", mode, err);
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_stft_features(const ttsa_plan* plan, const ttsa_batch* batch, const float* wav_dev,
+                                  float* lin_out_dev, float* mel_out_dev, uint32_t flags, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!wav_dev || (!lin_out_dev && !mel_out_dev)) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  if ((flags & TTSA_FEAT_PREEMPHASIS) && plan->cfg.preemphasis == 0.0)
+    return fail(TTSA_ERR_BAD_CONFIG, " !! Preemphasis is applied with factor 0.0. ");   // utils/audio.py:129-130
+  DeviceGuard guard(plan->device);
+  FrameArgs a{};
+  a.wav_in = wav_dev; a.lin_out = lin_out_dev; a.mel_out = mel_out_dev;
+  a.preemph = (flags & TTSA_FEAT_PREEMPHASIS) ? 1 : 0;
+  return launch_frames(plan, batch, MODE_ANALYSIS, OUT_FEATURES, false, a, (cudaStream_t)stream);
+}
+
+extern "C" int ttsa_stft(const ttsa_plan* plan, const ttsa_batch* batch, const float* wav_dev, float* stft_out_dev, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!wav_dev || !stft_out_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  DeviceGuard guard(plan->device);
+  FrameArgs a{};
+  a.wav_in = wav_dev; a.cplx_out = stft_out_dev;
+  return launch_frames(plan, batch, MODE_ANALYSIS, OUT_COMPLEX, false, a, (cudaStream_t)stream);
+}
+
+extern "C" int ttsa_istft(const ttsa_plan* plan, const ttsa_batch* batch, const float* stft_dev, float* wav_out_dev, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!stft_dev || !wav_out_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  DeviceGuard guard(plan->device);
+  FrameArgs a{};
+  a.cplx_in = stft_dev; a.wav_out = wav_out_dev;
+  return launch_frames(plan, batch, MODE_SYNTH, SRC_COMPLEX, false, a, (cudaStream_t)stream);
+}
+
+extern "C" size_t ttsa_deemphasis_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* batch) {
+  if (!plan || !batch) return 0;
+  return ((size_t)batch->chunk_off[batch->B] * 4 + 255) / 256 * 256 + 256;
+}
+
+extern "C" size_t ttsa_griffin_lim_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* batch) {
+  if (!plan || !batch) return 0;
+  const size_t wav = ((size_t)batch->total_samples * 4 + 255) / 256 * 256 + 256;
+  return 2 * wav + ttsa_deemphasis_workspace_bytes(plan, batch);
+}
+
+static int deemph_launch(const ttsa_plan* plan, const ttsa_batch* batch, const float* x, float* y, float* agg, cudaStream_t st) {
+  if (batch->max_chunks == 0) return TTSA_OK;
+  DeParams dp;
+  dp.p = (float)plan->cfg.preemphasis;
+  dp.log2p = (float)std::log2(plan->cfg.preemphasis);
+  dp.chunk_off = batch->d_chunk_off;
+  dim3 grid(batch->max_chunks, batch->B);
+  deemph_aggregate_kernel<<<grid, kDeThreads, 0, st>>>(batch->dev, dp, x, agg);
+  deemph_apply_kernel<<<grid, kDeThreads, 0, st>>>(batch->dev, dp, agg, x, y);
+  g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_deemphasis(const ttsa_plan* plan, const ttsa_batch* batch, const float* x_dev, float* y_dev,
+                               void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!x_dev || !y_dev || !workspace_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  if (plan->cfg.preemphasis == 0.0) return fail(TTSA_ERR_BAD_CONFIG, " !! Preemphasis is applied with factor 0.0. ");
+  if (plan->cfg.preemphasis < 0.0) return fail(TTSA_ERR_UNSUPPORTED, "negative preemphasis");
+  if (workspace_bytes < ttsa_deemphasis_workspace_bytes(plan, batch)) return fail(TTSA_ERR_WORKSPACE, "workspace too small");
+  DeviceGuard guard(plan->device);
+  return deemph_launch(plan, batch, x_dev, y_dev, (float*)workspace_dev, (cudaStream_t)stream);
+}
+
+extern "C" int ttsa_preemphasis(const ttsa_plan* plan, const ttsa_batch* batch, const float* x_dev, float* y_dev, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!x_dev || !y_dev || x_dev == y_dev) return fail(TTSA_ERR_BAD_ARG, "null or aliasing buffers");
+  if (plan->cfg.preemphasis == 0.0) return fail(TTSA_ERR_BAD_CONFIG, " !! Preemphasis is applied with factor 0.0. ");
+  DeviceGuard guard(plan->device);
+  int maxlen = 0;
+  for (int v : batch->wav_len) maxlen = std::max(maxlen, v);
+  dim3 grid(std::max(1, std::min(1024, (maxlen + 255) / 256)), batch->B);
+  preemphasis_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(batch->dev, (float)plan->cfg.preemphasis, x_dev, y_dev);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, const float* spec_dev, int spec_kind,
+                                int iters, const float* init_angles_dev, uint64_t seed, uint32_t flags,
+                                float* wav_out_dev, float* sc_log_dev, void* workspace_dev, size_t workspace_bytes,
+                                void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!spec_dev || !wav_out_dev || !workspace_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  if (spec_kind != TTSA_SPEC_MAGNITUDE && spec_kind != TTSA_SPEC_NORM_DB) return fail(TTSA_ERR_BAD_ARG, "bad spec_kind %d", spec_kind);
+  if (iters < 0) return fail(TTSA_ERR_BAD_ARG, "iters < 0");
+  if (workspace_bytes < ttsa_griffin_lim_workspace_bytes(plan, batch)) return fail(TTSA_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, ttsa_griffin_lim_workspace_bytes(plan, batch));
+  const bool deemph = (flags & TTSA_GL_DEEMPHASIS) != 0;
+  if (deemph && plan->cfg.preemphasis == 0.0) return fail(TTSA_ERR_BAD_CONFIG, " !! Preemphasis is applied with factor 0.0. ");
+  DeviceGuard guard(plan->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t wav_bytes = ((size_t)batch->total_samples * 4 + 255) / 256 * 256 + 256;
+  float* wsA = (float*)workspace_dev;
+  float* wsB = (float*)((char*)workspace_dev + wav_bytes);
+  float* agg = (float*)((char*)workspace_dev + 2 * wav_bytes);
+  // write k (0 = initial istft, 1..iters = iterations) goes to bufs[(k + s) & 1]; the last one must land in `last`
+  float* bufs[2];
+  float* last;
+  if (deemph) { bufs[0] = wsA; bufs[1] = wsB; last = (iters & 1) ? wsB : wsA; }
+  else        { bufs[iters & 1] = wav_out_dev; bufs[(iters & 1) ^ 1] = wsA; last = wav_out_dev; }
+  if (sc_log_dev && iters > 0) CUDA_TRY(cudaMemsetAsync(sc_log_dev, 0, (size_t)iters * batch->B * 2 * 4, st));
+
+  FrameArgs a{};
+  a.spec = spec_dev; a.angles = init_angles_dev; a.seed = seed; a.wav_out = bufs[0];
+  if (int rc = launch_frames(plan, batch, MODE_SYNTH, spec_kind, false, a, st)) return rc;
+  for (int i = 1; i <= iters; ++i) {
+    FrameArgs b{};
+    b.spec = spec_dev; b.wav_in = bufs[(i - 1) & 1]; b.wav_out = bufs[i & 1];
+    b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
+    if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st)) return rc;
+  }
+  if (bufs[iters & 1] != last) return fail(TTSA_ERR_CUDA, "internal: buffer rotation");
+  if (deemph) return deemph_launch(plan, batch, last, wav_out_dev, agg, st);
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_mel_to_linear(const ttsa_plan* plan, const ttsa_batch* batch, const float* mel_dev, int in_kind,
+                                  float* lin_out_dev, int out_kind, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!mel_dev || !lin_out_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  if ((in_kind != 0 && in_kind != 1) || (out_kind != 0 && out_kind != 1)) return fail(TTSA_ERR_BAD_ARG, "bad in/out kind");
+  if (batch->total_frames == 0) return TTSA_OK;
+  DeviceGuard guard(plan->device);
+  MelParams mp = plan->mel;
+  mp.rows = batch->total_frames;
+  dim3 grid((kF + kMtlBins - 1) / kMtlBins, (unsigned)((batch->total_frames + kMtlRows - 1) / kMtlRows));
+  const size_t smem = (size_t)mp.num_mels * (kMtlBins + kMtlRows) * 4;
+  mel_to_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mp, plan->d_pinvT, plan->ldp, mel_dev, lin_out_dev, in_kind, out_kind);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_linear_to_mel(const ttsa_plan* plan, const ttsa_batch* batch, const float* lin_dev, int in_kind,
+                                  float* mel_out_dev, int out_kind, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!lin_dev || !mel_out_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  if ((in_kind != 0 && in_kind != 1) || (out_kind != 0 && out_kind != 2)) return fail(TTSA_ERR_BAD_ARG, "bad in/out kind");
+  if (batch->total_frames == 0) return TTSA_OK;
+  DeviceGuard guard(plan->device);
+  MelParams mp = plan->mel;
+  mp.rows = batch->total_frames;
+  const unsigned grid = (unsigned)((batch->total_frames + 7) / 8);
+  linear_to_mel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp, plan->tb, lin_dev, mel_out_dev, in_kind, out_kind);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_pointwise(const ttsa_plan* plan, int op, const float* x_dev, float* y_dev, int64_t n, void* stream) {
+  if (!plan) return fail(TTSA_ERR_BAD_ARG, "null plan");
+  if (plan->device < 0) return fail(TTSA_ERR_NO_DEVICE, "host-only plan: no CUDA device bound; this library has no CPU path");
+  if (op < 0 || op > 3) return fail(TTSA_ERR_BAD_ARG, "bad op %d", op);
+  if (n < 0 || (n > 0 && (!x_dev || !y_dev))) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  if (n == 0) return TTSA_OK;
+  DeviceGuard guard(plan->device);
+  PwParams p = plan->pw;
+  p.op = op;
+  const long long blocks = (n + 255) / 256;
+  const int grid = (int)std::min<long long>(blocks, (long long)plan->num_sms * 16);
+  pointwise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, x_dev, y_dev, (long long)n);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_transpose(const float* in_dev, float* out_dev, int64_t rows, int64_t cols, void* stream) {
+  if (rows < 0 || cols < 0) return fail(TTSA_ERR_BAD_ARG, "negative shape");
+  if (rows == 0 || cols == 0) return TTSA_OK;
+  if (!in_dev || !out_dev || in_dev == out_dev) return fail(TTSA_ERR_BAD_ARG, "null or aliasing buffers");
+  const long long gy = (rows + 31) / 32, gx = (cols + 31) / 32;
+  if (gy > 65535) return fail(TTSA_ERR_UNSUPPORTED, "too many rows for one launch");
+  dim3 grid((unsigned)gx, (unsigned)gy), block(32, 8);
+  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in_dev, out_dev, rows, cols);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
