@@ -339,9 +339,11 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               sincospif((float)((kp * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
               Yp = make_float2((cp.x * cs - cp.y * sn) * kInvN, (cp.x * sn + cp.y * cs) * kInvN);
             } else {
+              // phases are given for the un-shifted frame: theta'[k] = theta[k] + 2 pi k lpad / n_fft
+              const int lpad = (kNfft - g.win) >> 1;
               const float Sk = spec_to_mag<SRC>(__ldg(a.spec + row * kF + k), g) * kInvN;
               const float Sp = spec_to_mag<SRC>(__ldg(a.spec + row * kF + kp), g) * kInvN;
-              float sk, ck, sp, cp;
+              float sk, ck, sp, cp, sn, cs;
               if (a.angles != nullptr) {
                 sincosf(__ldg(a.angles + row * kF + k), &sk, &ck);
                 sincosf(__ldg(a.angles + row * kF + kp), &sp, &cp);
@@ -349,8 +351,10 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
                 sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + k)), &sk, &ck);
                 sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + kp)), &sp, &cp);
               }
-              Yk = make_float2(Sk * ck, Sk * sk);
-              Yp = make_float2(Sp * cp, Sp * sp);
+              sincospif((float)((k * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
+              Yk = make_float2(Sk * (ck * cs - sk * sn), Sk * (ck * sn + sk * cs));
+              sincospif((float)((kp * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
+              Yp = make_float2(Sp * (cp * cs - sp * sn), Sp * (cp * sn + sp * cs));
             }
             if (MODE == MODE_SYNTH && l0 && k1 == 0) { Yk.y = 0.0f; Yp.y = 0.0f; }   // irfft ignores Im of DC / Nyquist
             // Z'2[k] = P + Q, Z'2[1024-k] = conj(P - Q),  P = Y[k] + conj(Y[1024-k]),  Q = conj(G_k) (Y[k] - conj(Y[1024-k]))
@@ -382,11 +386,13 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               sincospif((float)((512 * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
               Y = make_float2((c5.x * cs - c5.y * sn) * kInvN, (c5.x * sn + c5.y * cs) * kInvN);
             } else {
+              const int lpad = (kNfft - g.win) >> 1;
               const float S5 = spec_to_mag<SRC>(__ldg(a.spec + row * kF + 512), g) * kInvN;
-              float s5, c5;
+              float s5, c5, sn, cs;
               if (a.angles != nullptr) sincosf(__ldg(a.angles + row * kF + 512), &s5, &c5);
               else sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + 512)), &s5, &c5);
-              Y = make_float2(S5 * c5, S5 * s5);
+              sincospif((float)((512 * lpad) & (kNfft - 1)) * (2.0f / (float)kNfft), &sn, &cs);
+              Y = make_float2(S5 * (c5 * cs - s5 * sn), S5 * (c5 * sn + s5 * cs));
             }
             z512 = make_float2(2.0f * Y.x, -2.0f * Y.y);
           }
@@ -426,7 +432,8 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         const float* carry_old = smem + (cb ? g.sm_carry1 : g.sm_carry0);
         float* carry_new = smem + (cb ? g.sm_carry0 : g.sm_carry1);
         float* __restrict__ dst = a.wav_out + woff;
-        const int out_len = kNF * g.hop;
+        // the utterance's last tile also flushes what would be its carry (samples up to hop*(T-1) end there)
+        const int out_len = (t0 + kNF >= T) ? g.span_len : kNF * g.hop;
         for (int s = tid; s < g.span_len; s += kThreads) {
           const int q = (int)(((float)s + 0.5f) * g.inv_hop);
           const int rr = s - q * g.hop;
