@@ -186,6 +186,23 @@ def test_large_batch_segments_deterministic_and_match_oracle():
     assert snr_db(lay.split_wav(y1)[37].cpu().numpy(), y_single[:275 * (T - 1)].cpu().numpy()) >= 120.0
 
 
+def test_generic_geometry_kernel_class():
+    """win 1764 / hop 275 (80 ms window): more than 5 taps per hop residue and 28 non-zero packed rows -> the generic
+    (NZ = 32) kernel class; and win 2048 == n_fft."""
+    for flm in (80.0, 92.88):
+        audio = dict(MAIN_AUDIO, frame_length_ms=flm, griffin_lim_iters=4)
+        ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+        assert ap.win_length in (1764, 2048)
+        y = synth_speech_like(3, n_samples=275 * 21)
+        spec, spec_o = ap.spectrogram(y), orc.spectrogram(y)
+        assert np.mean(np.abs(spec - spec_o) <= FWD_TOL) >= 0.995
+        ang = (2 * np.pi * np.random.default_rng(1).random(spec_o.shape)).astype(np.float32)
+        w, sc = ap.inv_spectrogram(spec_o.astype(np.float32), init_angles=ang, return_sc=True)
+        wo, sco = orc.inv_spectrogram(spec_o.astype(np.float32), init_angles=ang, return_sc=True)
+        assert snr_db(wo, w) >= GL_SNR_DB, snr_db(wo, w)
+        np.testing.assert_allclose(sc, sco, rtol=SC_RTOL)
+
+
 def test_device_rng_phases():
     audio = dict(MAIN_AUDIO, griffin_lim_iters=6)
     ap = _ap(audio)

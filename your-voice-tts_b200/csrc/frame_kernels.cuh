@@ -24,6 +24,7 @@ enum { OUT_COMPLEX = 0, OUT_FEATURES = 1 };               // ANALYSIS output kin
 
 struct FrameArgs {
   const float* spec;      // [sum_T, F]      GL_ITER / SYNTH (mag or normalised dB)
+  const float* spec_end;  // one past the last element of spec (bounds for the 16-byte row copies)
   const float* angles;    // [sum_T, F]      SYNTH: initial phases in radians, or nullptr -> counter RNG
   const float* cplx_in;   // [sum_T, F, 2]   SYNTH with SRC_COMPLEX
   const float* wav_in;    // packed wav      GL_ITER (previous y) / ANALYSIS
@@ -56,9 +57,9 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigne
 // ---------------------------------------------------------------------------------------------------------
 // per-warp transform passes
 // ---------------------------------------------------------------------------------------------------------
-// v[n2] = z[lane + 32 n2]  ->  v[k1] = Z[32 k1 + lane]       (forward, e^{-j})
+// v[n2] = z[lane + 32 n2]  ->  v[k1] = Z[32 k1 + lane]       (forward, e^{-j}); second pass left to the caller
 template <int NZ>
-__device__ __forceinline__ void fwd_passes(float2 (&v)[32], float2* buf, const float2* tw, int lane) {
+__device__ __forceinline__ void fwd_pass1_exchange(float2 (&v)[32], float2* buf, const float2* tw, int lane) {
   fft32<false, NZ>(v);                                   // over n2 -> k2
 #pragma unroll
   for (int k2 = 1; k2 < 32; ++k2) {                      // W_1024^(lane * k2)
@@ -77,7 +78,36 @@ __device__ __forceinline__ void fwd_passes(float2 (&v)[32], float2* buf, const f
     v[n1] = make_float2(q.x, q.y);
     v[n1 + 1] = make_float2(q.z, q.w);
   }
-  fft32<false, 32>(v);                                   // over n1 -> k1
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Asynchronous copy of one spectrogram row (kF floats, 4-byte aligned) into the warp's exchange buffer with 16-byte
+// chunks taken from the enclosing 16-byte-aligned range; element k lands at dst[off + k], off = returned value.
+// Chunks that would touch memory outside [lo, hi) fall back to 4-byte copies of the in-range elements.
+__device__ __forceinline__ int row_to_smem_async(float* dst, const float* row_ptr, const float* lo, const float* hi, int lane) {
+  const int off = (int)((reinterpret_cast<unsigned long long>(row_ptr) >> 2) & 3ull);
+  const float* base = row_ptr - off;                      // 16-byte aligned
+  const int nchunks = (off + kF + 3) >> 2;
+  for (int c = lane; c < nchunks; c += 32) {
+    const float* gsrc = base + 4 * c;
+    if (gsrc >= lo && gsrc + 4 <= hi) {
+      cp_async16(dst + 4 * c, gsrc);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (gsrc + e >= lo && gsrc + e < hi) cp_async4(dst + 4 * c + e, gsrc + e);
+    }
+  }
+  return off;
 }
 
 // v[k1] = Z'[32 k1 + lane]  ->  v[n2] = z'[lane + 32 n2]      (inverse, e^{+j}, unnormalised)
@@ -128,6 +158,8 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr float kInvN = 1.0f / (float)kNfft;
+  // taps of one frame falling on the same residue mod hop: ceil(win / hop); 5 for every shipped geometry
+  constexpr int ND = (NZ <= 20) ? 5 : kNF + 1;
 
   float2* const buf = reinterpret_cast<float2*>(smem + warp * kBufFloats);
   float* const plane0 = smem + g.sm_plane0;
@@ -188,14 +220,23 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
       if constexpr (MODE != MODE_SYNTH) {
         // stage the contiguous input span, de-interleaved by parity (conflict-free re/im frame loads)
         const float* __restrict__ src = a.wav_in + woff;
-        for (int s = tid; s < g.span_len; s += kThreads) {
-          const int j = reflect_index(i0 + s, L);
-          float val = __ldg(src + j);
-          if (MODE == MODE_ANALYSIS && a.preemph) {
-            const float prev = j > 0 ? __ldg(src + j - 1) : 0.0f;
-            val = fmaf(-g.preemph, prev, val);
+        if (i0 >= 1 && i0 + g.span_len <= L) {                       // interior span: no reflection
+          const float* __restrict__ sp = src + i0;
+          for (int s = tid; s < g.span_len; s += kThreads) {
+            float val = __ldg(sp + s);
+            if (MODE == MODE_ANALYSIS && a.preemph) val = fmaf(-g.preemph, __ldg(sp + s - 1), val);
+            ((s & 1) ? plane1 : plane0)[s >> 1] = val;
           }
-          ((s & 1) ? plane1 : plane0)[s >> 1] = val;
+        } else {
+          for (int s = tid; s < g.span_len; s += kThreads) {
+            const int j = reflect_index(i0 + s, L);
+            float val = __ldg(src + j);
+            if (MODE == MODE_ANALYSIS && a.preemph) {
+              const float prev = j > 0 ? __ldg(src + j - 1) : 0.0f;
+              val = fmaf(-g.preemph, prev, val);
+            }
+            ((s & 1) ? plane1 : plane0)[s >> 1] = val;
+          }
         }
         __syncthreads();
       }
@@ -205,6 +246,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         const long long row = frow0 + t;
         const bool own = t >= ja * kNF;            // warm-up frames are copies of another segment's frames
         float2 v[32];
+        int s_off = 0;
         // ------------------------------------------------------------------ forward half
         if constexpr (MODE != MODE_SYNTH) {
           const int o = warp * g.hop;
@@ -221,7 +263,14 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               v[n2] = make_float2(0.0f, 0.0f);
             }
           }
-          fwd_passes<NZ>(v, buf, tw, lane);
+          fwd_pass1_exchange<NZ>(v, buf, tw, lane);
+          if constexpr (MODE == MODE_GL_ITER) {
+            // the exchange buffer is idle until the inverse transform: stream this frame's |S| row into it now,
+            // so that the HBM latency hides behind the second FFT pass
+            __syncwarp();
+            s_off = row_to_smem_async(reinterpret_cast<float*>(buf), a.spec + row * kF, a.spec, a.spec_end, lane);
+          }
+          fft32<false, 32>(v);                                   // over n1 -> k1
         }
 
         // ------------------------------------------------------------------ per-bin step on conjugate pairs
@@ -302,13 +351,18 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
           // ---------------------------------------------------------------- GL_ITER / SYNTH: build Y, then Z'
           float2 snd[16];
           float2 z512 = make_float2(0.0f, 0.0f);
+          const float* srow = reinterpret_cast<const float*>(buf) + s_off;
+          if constexpr (MODE == MODE_GL_ITER) {
+            cp_async_wait_all();
+            __syncwarp();
+          }
 #pragma unroll
           for (int k1 = 0; k1 < 16; ++k1) {
             const int k = 32 * k1 + lane, kp = 1024 - k;
             float2 Yk, Yp;
             if constexpr (MODE == MODE_GL_ITER) {
-              const float Sk = spec_to_mag<SRC>(__ldg(a.spec + row * kF + k), g);
-              const float Sp = spec_to_mag<SRC>(__ldg(a.spec + row * kF + kp), g);
+              const float Sk = spec_to_mag<SRC>(srow[k], g);
+              const float Sp = spec_to_mag<SRC>(srow[kp], g);
               const float2 A = v[k1], B = r[k1];
               const float2 E2 = make_float2(A.x + B.x, A.y - B.y);
               const float2 D2 = make_float2(A.x - B.x, A.y + B.y);
@@ -368,7 +422,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
           if (l0) {   // k = 512 (self-paired): X = conj(Z[512]), Z'2 = 2 conj(Y)
             float2 Y;
             if constexpr (MODE == MODE_GL_ITER) {
-              const float S5 = spec_to_mag<SRC>(__ldg(a.spec + row * kF + 512), g);
+              const float S5 = spec_to_mag<SRC>(srow[512], g);
               const float2 X = make_float2(v[16].x, -v[16].y);
               const float m = X.x * X.x + X.y * X.y;
               const float im = rsqrtf(m);
@@ -434,37 +488,50 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         float* __restrict__ dst = a.wav_out + woff;
         // the utterance's last tile also flushes what would be its carry (samples up to hop*(T-1) end there)
         const int out_len = (t0 + kNF >= T) ? g.span_len : kNF * g.hop;
-        for (int s = tid; s < g.span_len; s += kThreads) {
-          const int q = (int)(((float)s + 0.5f) * g.inv_hop);
-          const int rr = s - q * g.hop;
-          float sum = (has_carry && s < g.carry_len) ? carry_old[s] : 0.0f;
-          for (int d = 0, m = rr; m < g.win; ++d, m += g.hop) {
-            const int f = q - d;
-            if (f >= fv_lo && f < fv_hi) sum += smem[f * kBufFloats + m];
+        // each thread owns a residue rr (mod hop): acc[j] is span sample j*hop + rr; frame f adds its taps
+        // rr + d*hop (d < ND) to acc[f + d].  All register indices are static; lanes read consecutive addresses.
+        for (int rr = tid; rr < g.hop; rr += kThreads) {
+          float acc[kNF + ND - 1];
+#pragma unroll
+          for (int j = 0; j < kNF + ND - 1; ++j) {
+            const int sidx = j * g.hop + rr;
+            acc[j] = (has_carry && sidx < g.carry_len) ? carry_old[sidx] : 0.0f;
           }
-          if (s < out_len) {
-            const int i = i0 + s;
-            if (write_out && i >= 0 && i < L) {
-              const int dmax = (g.win - 1 - rr) / g.hop;
-              const int tlo = t0 + q - dmax, thi = t0 + q;
-              float inv;
-              if (tlo >= 0 && thi <= T - 1) {
-                inv = pw[rr];
-              } else {
-                float ws = 0.0f;
-                for (int d = 0, m = rr; m < g.win; ++d, m += g.hop) {
-                  const int tt = t0 + q - d;
-                  if (tt >= 0 && tt < T) {
-                    const float wv = (m & 1) ? wO[m >> 1] : wE[m >> 1];
-                    ws = fmaf(wv, wv, ws);
-                  }
-                }
-                inv = ws > 1.17549435e-38f ? 1.0f / ws : 1.0f;   // librosa: divide only where wss > tiny
-              }
-              dst[i] = sum * inv;
+#pragma unroll
+          for (int f = 0; f < kNF; ++f) {
+            if (f >= fv_lo && f < fv_hi) {
+              const float* sl = smem + f * kBufFloats + rr;
+#pragma unroll
+              for (int d = 0; d < ND; ++d)
+                if (rr + d * g.hop < g.win) acc[f + d] += sl[d * g.hop];
             }
-          } else {
-            carry_new[s - out_len] = sum;
+          }
+          const int dmax = (g.win - 1 - rr) / g.hop;
+          const float inv_int = pw[rr];
+#pragma unroll
+          for (int j = 0; j < kNF + ND - 1; ++j) {
+            const int sidx = j * g.hop + rr;
+            if (sidx >= g.span_len) continue;
+            if (sidx < out_len) {
+              const int i = i0 + sidx;
+              if (write_out && i >= 0 && i < L) {
+                float inv = inv_int;
+                if (t0 + j - dmax < 0 || t0 + j > T - 1) {          // some overlapping frame does not exist
+                  float ws = 0.0f;
+                  for (int d = 0, m = rr; m < g.win; ++d, m += g.hop) {
+                    const int tt = t0 + j - d;
+                    if (tt >= 0 && tt < T) {
+                      const float wv = (m & 1) ? wO[m >> 1] : wE[m >> 1];
+                      ws = fmaf(wv, wv, ws);
+                    }
+                  }
+                  inv = ws > 1.17549435e-38f ? 1.0f / ws : 1.0f;    // librosa: divide only where wss > tiny
+                }
+                dst[i] = acc[j] * inv;
+              }
+            } else {
+              carry_new[sidx - out_len] = acc[j];
+            }
           }
         }
         has_carry = true;

@@ -173,7 +173,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->cfg = c;
   p->device = device;
   build_geo(c, p->geo);
-  p->nz = (p->geo.half <= 20 * 32) ? 20 : 32;
+  // kernel class 20: <= 20 non-zero rows of packed input and <= 5 taps per residue mod hop (every shipped geometry)
+  p->nz = (p->geo.half <= 20 * 32 && (c.win_length + c.hop_length - 1) / c.hop_length <= 5) ? 20 : 32;
   if ((size_t)p->geo.sm_total * 4 > 227 * 1024) {
     delete p;
     return fail(TTSA_ERR_UNSUPPORTED, "hop/win need %d bytes of shared memory per CTA", p->geo.sm_total * 4);
@@ -546,7 +547,8 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
   if (int rc = launch_frames(plan, batch, MODE_SYNTH, spec_kind, false, a, st)) return rc;
   for (int i = 1; i <= iters; ++i) {
     FrameArgs b{};
-    b.spec = spec_dev; b.wav_in = bufs[(i - 1) & 1]; b.wav_out = bufs[i & 1];
+    b.spec = spec_dev; b.spec_end = spec_dev + (size_t)batch->total_frames * kF;
+    b.wav_in = bufs[(i - 1) & 1]; b.wav_out = bufs[i & 1];
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
     if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st)) return rc;
   }
