@@ -173,8 +173,10 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->cfg = c;
   p->device = device;
   build_geo(c, p->geo);
-  // kernel class 20: <= 20 non-zero rows of packed input and <= 5 taps per residue mod hop (every shipped geometry)
-  p->nz = (p->geo.half <= 20 * 32 && (c.win_length + c.hop_length - 1) / c.hop_length <= 5) ? 20 : 32;
+  // kernel class 20 ("standard"): <= 20 non-zero rows of packed input, <= 5 taps per residue mod hop, and 5*hop floats
+  // fit the zero-padded overlap-add slot.  True for every shipped geometry (275/1102, 200/800, 300/1200).
+  p->nz = (p->geo.half <= 20 * 32 && (c.win_length + c.hop_length - 1) / c.hop_length <= 5 &&
+           5 * c.hop_length <= kBufFloats) ? 20 : 32;
   if ((size_t)p->geo.sm_total * 4 > 227 * 1024) {
     delete p;
     return fail(TTSA_ERR_UNSUPPORTED, "hop/win need %d bytes of shared memory per CTA", p->geo.sm_total * 4);
