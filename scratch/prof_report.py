@@ -4,8 +4,9 @@ exec(open('scratch/sass_lines.py').read().split("tot=sum")[0].replace("sass, ncu
 lines=open('your-voice-tts_b200/csrc/frame_kernels.cuh').read().split('\n')
 def find(s): 
     return next(i+1 for i,l in enumerate(lines) if s in l)
-marks=[('setup',0),('stage',find('stage the contiguous input span')),('frame load',find('forward half')),('shfl1',find('per-bin step on conjugate pairs')),
-       ('middle',find('GL_ITER / SYNTH: build Y')),('shfl2',find('hand the partner its half')),('inverse/slot',find('inverse half')),('OLA',find('overlap-add + 1/wss + store')),('sc',find('if constexpr (MODE == MODE_GL_ITER && SC)'))]
+marks=[('setup',0),('stage helpers',find('span staging helpers')),('tile loop/stage',find('previous segment is done with planes')),('frame load',find('window the frame')),
+       ('middle',find('per-bin step -> conj')),('shfl2',find('hand the partner its half')),('transform glue',find('1024-point transform, 32 x 32')),('analysis out',find('spectrum out')),
+       ('slot store',find("window -> the warp's overlap-add slot")),('post-frame sync/stage_load',find('slots complete; planes consumed')),('OLA',find('overlap-add + 1/(N wss) + store')),('stage_store/sync',find('if (have_next) stage_store')),('sc',find('if constexpr (MODE == MODE_GL_ITER && SC)'))]
 helper_end=find('// the kernel')
 def region(l):
     if l is None: return 'none'

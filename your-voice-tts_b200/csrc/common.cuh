@@ -10,14 +10,17 @@ constexpr int kM = 1024;             // packed complex transform length
 constexpr int kF = 1025;             // bins
 constexpr int kNF = 8;               // frames per tile == warps per CTA (one warp owns one frame)
 constexpr int kThreads = kNF * 32;
-constexpr int kRowStride = 34;       // float2 row stride of the 32x32 exchange buffer (conflict-free 64b writes / 128b reads)
-constexpr int kBufFloats = 32 * kRowStride * 2;   // per-warp exchange buffer, reused as the warp's overlap-add slot
+constexpr int kRowFloats = 68;       // row stride of the 32x32 exchange buffer: [re 0..31 | im 0..31 | pad], 68 = 4 mod 32
+                                     // keeps both the 32-bit column writes and the 128-bit row reads conflict-free
+constexpr int kBufFloats = 32 * kRowFloats;       // per-warp exchange buffer, reused as the warp's overlap-add slot
+constexpr int kSlotPlane = 1040;     // slot = even-sample plane + odd-sample plane (16 banks apart)
 
 // Geometry and scalar constants, passed by value to every frame kernel.
 struct Geo {
   int hop, win, off0;        // off0 = n_fft/2 - (n_fft - win)/2: sample offset of window tap 0 relative to t*hop
   int half;                  // ceil(win / 2): number of packed complex inputs that are not identically zero
-  int wlen;                  // half rounded up to 32: length of the even/odd window tables held in shared memory
+  int wlen;                  // floats in each paired window table held in shared memory (kernel class rows * 32)
+  int plane_len;             // floats in each parity plane of the staged span (tail beyond the span stays zero)
   int carry_len;             // win - hop
   int span_len;              // (kNF-1)*hop + win
   int nwarm;                 // (win-1)/hop: earlier frames overlapping a segment's first owned sample
@@ -34,10 +37,12 @@ struct Geo {
 
 // Plan-owned device tables.
 struct Tables {
-  const float2* tw;      // [32*32]  W_1024^(a*b) = (cos, -sin)(2 pi a b / 1024)
-  const float2* g;       // [512]    G_k = -j * W_2048^k = (-sin, -cos)(pi k / 1024)
-  const float* wE;       // [1024]   w[2q]   (zero padded)
-  const float* wO;       // [1024]   w[2q+1]
+  const float4* tw4;     // [16][32]  (wr(2m), wr(2m+1), wi(2m), wi(2m+1)),  w(k) = W_1024^(lane*k) = (cos, -sin)(2 pi lane k / 1024)
+  const float4* g4;      // [8][32]   (gx(2m), gx(2m+1), gy(2m), gy(2m+1)),  g(k1) = -j W_2048^(32 k1 + lane)
+  const float2* wE2;     // [16][32]  (w[2q], w[2(q+32)]),  q = lane + 64 m   (even window taps, paired for two packed rows)
+  const float2* wO2;     // [16][32]  (w[2q+1], w[2(q+32)+1])
+  const float* wE;       // [1024]    w[2q]   (zero padded)
+  const float* wO;       // [1024]    w[2q+1]
   const float* pw;       // [hop]    1 / sum_q w[r + q*hop]^2   (interior window-sum-square, periodic in hop)
   // sparse mel basis (CSR over mel rows; each row is one contiguous run of bins)
   const int* mel_lo;     // [num_mels]

@@ -14,11 +14,16 @@
 // output and MODE_SYNTH with complex input or injected phases apply the ramp explicitly.)
 //
 // The inverse transform runs through the SAME forward code: ifft(Z) = conj(fft(conj(Z))); the per-bin step emits
-// conj(Z') and the final window multiply negates the imaginary parts.  The transform body therefore exists once in
-// the instruction stream (a rolled loop of four 32-point passes), which keeps the kernel inside the instruction cache.
+// conj(Z') and the synthesis window (applied inside the overlap-add) carries the sign of the imaginary parts.  The
+// transform body therefore exists once in the instruction stream (a rolled loop of four 32-point passes), which keeps
+// the kernel inside the instruction cache.
+//
+// All per-frame arithmetic runs on packed fp32 pairs (FFMA2/FADD2/FMUL2, fft32p.cuh): a thread's 32 complex values are
+// 16 (re, re) + 16 (im, im) register pairs.  The FP32 lane work is unchanged, but the packed form halves the issue
+// slots it needs, and the kernel is issue-bound (measured: FP pipe 39 % busy at 64 % issue utilisation before packing).
 #pragma once
 #include "common.cuh"
-#include "fft32.cuh"
+#include "fft32p.cuh"
 
 namespace ttsa {
 
@@ -118,33 +123,47 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 shfl2(float a, float b, int srclane) {
+  return make_float2(__shfl_sync(0xffffffffu, a, srclane), __shfl_sync(0xffffffffu, b, srclane));
+}
+
 template <int MODE, int SRC, int NZ, bool SC>
 __global__ void __launch_bounds__(kThreads, 2)
 frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr float kInvN = 1.0f / (float)kNfft;
-  // kernel class: NZ 20 = "standard" geometry (<= 5 window taps per residue mod hop, 5*hop floats fit a slot, so slots
-  // are zero padded to 5*hop and the overlap-add needs no tap predicates); NZ 32 = anything up to win <= 9*hop.
+  constexpr float kTiny = 1e-37f;
+  // kernel class: NZ 20 = "standard" geometry (<= 20 non-zero packed rows, <= 5 window taps per residue mod hop);
+  // NZ 32 = anything up to win <= 9*hop.
   constexpr bool kStd = (NZ <= 20);
   constexpr int ND = kStd ? 5 : kNF + 1;
   constexpr int kStage = 13;                      // span samples per thread prefetched through registers (13*256 >= 7*hop+win
                                                   // for every shipped geometry; any remainder is copied synchronously)
 
-  float2* const buf = reinterpret_cast<float2*>(smem + warp * kBufFloats);
+  float* const buf = smem + warp * kBufFloats;
   float* const plane0 = smem + g.sm_plane0;
   float* const plane1 = smem + g.sm_plane1;
   float* const carry = smem + g.sm_carry0;
-  float* const wE = smem + g.sm_wE;
-  float* const wO = smem + g.sm_wO;
+  const float2* const wE2 = reinterpret_cast<const float2*>(smem + g.sm_wE);
+  const float2* const wO2 = reinterpret_cast<const float2*>(smem + g.sm_wO);
   float* const pw = smem + g.sm_pw;
-  float2* const tw = reinterpret_cast<float2*>(smem + g.sm_tw);
-  float2* const gt = reinterpret_cast<float2*>(smem + g.sm_g);
+  const float4* const tw4 = reinterpret_cast<const float4*>(smem + g.sm_tw);
+  const float4* const g4 = reinterpret_cast<const float4*>(smem + g.sm_g);
 
-  // plan tables -> shared memory (once per persistent CTA)
-  for (int i = tid; i < 1024; i += kThreads) tw[i] = tb.tw[i];
-  for (int i = tid; i < 512; i += kThreads) gt[i] = tb.g[i];
-  for (int i = tid; i < g.wlen; i += kThreads) { wE[i] = tb.wE[i]; wO[i] = tb.wO[i]; }
+  // plan tables -> shared memory (once per persistent CTA); staged-span planes start zeroed (their tails stay zero)
+  for (int i = tid; i < 512; i += kThreads) reinterpret_cast<float4*>(smem + g.sm_tw)[i] = tb.tw4[i];
+  for (int i = tid; i < 256; i += kThreads) reinterpret_cast<float4*>(smem + g.sm_g)[i] = tb.g4[i];
+  for (int i = tid; i < g.wlen / 2; i += kThreads) {
+    reinterpret_cast<float2*>(smem + g.sm_wE)[i] = tb.wE2[i];
+    reinterpret_cast<float2*>(smem + g.sm_wO)[i] = tb.wO2[i];
+  }
+  for (int i = tid; i < g.plane_len; i += kThreads) { plane0[i] = 0.0f; plane1[i] = 0.0f; }
   if constexpr (MODE != MODE_ANALYSIS)
     for (int i = tid; i < g.hop; i += kThreads) pw[i] = tb.pw[i] * kInvN;     // 1/wss and the 1/n_fft of the inverse FFT
 
@@ -245,115 +264,134 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
       if (t < T && t >= first_needed) {
         const long long row = frow0 + t;
         const bool own = t >= ja * kNF;            // warm-up frames are copies of another segment's frames
-        float2 v[32];
+        // 32 complex values per thread as packed pairs: R[m] = (re[2m], re[2m+1]), I[m] = (im[2m], im[2m+1])
+        float2 R[16], I[16];
         int s_off = 0;
         constexpr int kHalfBegin = (MODE == MODE_SYNTH) ? 1 : 0;
         constexpr int kHalfEnd = (MODE == MODE_ANALYSIS) ? 1 : 2;
+        const int partner = (32 - lane) & 31;
+        const bool l0 = lane == 0;
+        const int lpad = (kNfft - g.win) >> 1;
 
 #pragma unroll 1
         for (int half = kHalfBegin; half < kHalfEnd; ++half) {
           if (half == 0) {
             // ---------------------------------------------------------------- window the frame
+            // element n2 of this lane is z[lane + 32 n2] = x[2q] + j x[2q+1], q = lane + 32 n2; rows past the
+            // window read zero window taps (the planes' tails are zero, so the products are exact zeros)
             if constexpr (MODE != MODE_SYNTH) {
               const int o = warp * g.hop;
-              const float* re_p = (o & 1) ? plane1 + ((o - 1) >> 1) : plane0 + (o >> 1);
-              const float* im_p = (o & 1) ? plane0 + ((o + 1) >> 1) : plane1 + (o >> 1);
+              const float* re_p = ((o & 1) ? plane1 + ((o - 1) >> 1) : plane0 + (o >> 1)) + lane;
+              const float* im_p = ((o & 1) ? plane0 + ((o + 1) >> 1) : plane1 + (o >> 1)) + lane;
 #pragma unroll
-              for (int n2 = 0; n2 < 32; ++n2) {
-                if (n2 < NZ) {
-                  const int q = lane + 32 * n2;
-                  const bool in = q < g.half;
-                  v[n2].x = in ? re_p[q] * wE[q] : 0.0f;
-                  v[n2].y = in ? im_p[q] * wO[q] : 0.0f;
+              for (int m = 0; m < 16; ++m) {
+                if (2 * m < NZ) {
+                  R[m] = __fmul2_rn(make_float2(re_p[64 * m], re_p[64 * m + 32]), wE2[m * 32 + lane]);
+                  I[m] = __fmul2_rn(make_float2(im_p[64 * m], im_p[64 * m + 32]), wO2[m * 32 + lane]);
                 } else {
-                  v[n2] = make_float2(0.0f, 0.0f);
+                  R[m] = make_float2(0.0f, 0.0f);
+                  I[m] = make_float2(0.0f, 0.0f);
                 }
               }
             }
           } else if constexpr (MODE != MODE_ANALYSIS) {
             // ---------------------------------------------------------------- per-bin step -> conj(Z')
-            // lane holds Z[32 k1 + lane]; bin k pairs with 1024 - k, held by lane (32 - lane) & 31.  Each lane
-            // processes the 16 pairs whose first member is its own register k1 < 16.
-            const int partner = (32 - lane) & 31;
-            const bool l0 = lane == 0;
-            const int lpad = (kNfft - g.win) >> 1;
-            float2 r[16];
+            // lane holds Z[32 k1 + lane]; bin k pairs with 1024 - k, held by lane (32 - lane) & 31 in register
+            // 31 - k1 (lane 0: its own register 32 - k1).  Each lane processes the 16 pairs whose first member is its
+            // own register k1 < 16, two pairs (k1 = 2m, 2m+1) per packed instruction.
+            float2 BR[8], BI[8];
             if constexpr (MODE == MODE_GL_ITER) {
-#pragma unroll
-              for (int k1 = 0; k1 < 16; ++k1) {
-                const float2 sv = l0 ? v[(32 - k1) & 31] : v[31 - k1];
-                r[k1].x = __shfl_sync(0xffffffffu, sv.x, partner);
-                r[k1].y = __shfl_sync(0xffffffffu, sv.y, partner);
-              }
+              static_for<0, 8>([&](auto mc) {
+                constexpr int m = decltype(mc)::value;
+                constexpr int ms = (m == 0) ? 0 : 16 - m;       // lane 0, k1 = 2m: own register (32 - 2m) & 31 = 2 * ms
+                const float s0r = l0 ? R[ms].x : R[15 - m].y, s0i = l0 ? I[ms].x : I[15 - m].y;
+                const float s1r = l0 ? R[15 - m].y : R[15 - m].x, s1i = l0 ? I[15 - m].y : I[15 - m].x;
+                BR[m] = shfl2(s0r, s1r, partner);
+                BI[m] = shfl2(s0i, s1i, partner);
+              });
               cp_async_wait_all();                   // this frame's |S| row (issued between the two forward passes)
               __syncwarp();
             }
-            const float* srow = reinterpret_cast<const float*>(buf) + s_off;
-            float2 snd[16];
+            const float* srow = buf + s_off;
+            float2 SR[8], SI[8];
             float2 z512 = make_float2(0.0f, 0.0f);
-#pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) {
-              const int k = 32 * k1 + lane, kp = 1024 - k;
-              float2 Yk, Yp;
+            static_for<0, 8>([&](auto mc) {
+              constexpr int m = decltype(mc)::value;
+              const int k0 = 64 * m + lane;                      // bins k0 (k1 = 2m) and k0 + 32 (k1 = 2m+1); partners 1024 - k
+              const float4 gq = g4[m * 32 + lane];
+              const float2 GX = make_float2(gq.x, gq.y), GY = make_float2(gq.z, gq.w);
+              float2 YkR, YkI, YpR, YpI;
               if constexpr (MODE == MODE_GL_ITER) {
-                const float Sk = spec_to_mag<SRC>(srow[k], g);
-                const float Sp = spec_to_mag<SRC>(srow[kp], g);
-                const float2 A = v[k1], B = r[k1];
-                const float2 E2 = make_float2(A.x + B.x, A.y - B.y);
-                const float2 D2 = make_float2(A.x - B.x, A.y + B.y);
-                const float2 Tt = cmul(gt[k], D2);
-                const float2 Xk = make_float2(E2.x + Tt.x, E2.y + Tt.y);          // 2 X[k]
-                const float2 Xp = make_float2(E2.x - Tt.x, -(E2.y - Tt.y));       // 2 X[1024-k]
-                const float mk = Xk.x * Xk.x + Xk.y * Xk.y;
-                const float mp = Xp.x * Xp.x + Xp.y * Xp.y;
-                const float ik = rsqrtf(fmaxf(mk, 1e-37f)), ip = rsqrtf(fmaxf(mp, 1e-37f));
-                const float fk = Sk * ik, fp = Sp * ip;
+                const float2 Sk = make_float2(spec_to_mag<SRC>(srow[k0], g), spec_to_mag<SRC>(srow[k0 + 32], g));
+                const float2 Sp = make_float2(spec_to_mag<SRC>(srow[1024 - k0], g), spec_to_mag<SRC>(srow[992 - k0], g));
+                const float2 E2R = __fadd2_rn(R[m], BR[m]), E2I = __fadd2_rn(I[m], neg2(BI[m]));
+                const float2 D2R = __fadd2_rn(R[m], neg2(BR[m])), D2I = __fadd2_rn(I[m], BI[m]);
+                // 2 X[k] = E2 + G D2 ;  2 X[1024-k] = conj(E2 - G D2) = conj(2 E2 - 2 X[k])
+                float2 XkR = __ffma2_rn(GX, D2R, E2R);
+                XkR = __ffma2_rn(neg2(GY), D2I, XkR);
+                float2 XkI = __ffma2_rn(GX, D2I, E2I);
+                XkI = __ffma2_rn(GY, D2R, XkI);
+                const float2 XpR = __ffma2_rn(E2R, splat(2.0f), neg2(XkR));
+                const float2 XpI = __ffma2_rn(E2I, splat(-2.0f), XkI);
+                const float2 mk = __ffma2_rn(XkI, XkI, __fmul2_rn(XkR, XkR));
+                const float2 mp = __ffma2_rn(XpI, XpI, __fmul2_rn(XpR, XpR));
+                const float2 ik = make_float2(rsqrt_fast(fmaxf(mk.x, kTiny)), rsqrt_fast(fmaxf(mk.y, kTiny)));
+                const float2 ip = make_float2(rsqrt_fast(fmaxf(mp.x, kTiny)), rsqrt_fast(fmaxf(mp.y, kTiny)));
+                const float2 fk = __fmul2_rn(Sk, ik), fp = __fmul2_rn(Sp, ip);
                 // Y = S X/|X|;  np.angle(0) = 0  ->  Y = S  (the imaginary part is 0 * finite = 0 already)
-                Yk = make_float2(mk > 1e-37f ? Xk.x * fk : Sk, Xk.y * fk);
-                Yp = make_float2(mp > 1e-37f ? Xp.x * fp : Sp, Xp.y * fp);
+                YkR = __fmul2_rn(XkR, fk); YkI = __fmul2_rn(XkI, fk);
+                YpR = __fmul2_rn(XpR, fp); YpI = __fmul2_rn(XpI, fp);
+                YkR.x = mk.x > kTiny ? YkR.x : Sk.x; YkR.y = mk.y > kTiny ? YkR.y : Sk.y;
+                YpR.x = mp.x > kTiny ? YpR.x : Sp.x; YpR.y = mp.y > kTiny ? YpR.y : Sp.y;
                 if (SC && own) {
-                  const float dk = 0.5f * mk * ik - Sk, dp = 0.5f * mp * ip - Sp;
-                  sc_num += dk * dk + dp * dp;
-                  sc_den += Sk * Sk + Sp * Sp;
+                  const float2 dk = __ffma2_rn(__fmul2_rn(mk, ik), splat(0.5f), neg2(Sk));   // |X| - S
+                  const float2 dp = __ffma2_rn(__fmul2_rn(mp, ip), splat(0.5f), neg2(Sp));
+                  sc_num += dk.x * dk.x + dk.y * dk.y + dp.x * dp.x + dp.y * dp.y;
+                  sc_den += Sk.x * Sk.x + Sk.y * Sk.y + Sp.x * Sp.x + Sp.y * Sp.y;
                 }
-              } else if constexpr (SRC == SRC_COMPLEX) {
-                // shifted coordinates: Y'[k] = Y[k] * exp(+j 2 pi k lpad / n_fft)
-                const float2* in = reinterpret_cast<const float2*>(a.cplx_in) + row * kF;
-                Yk = cmul(in[k], shift_phasor(k, lpad, 1.0f));
-                Yp = cmul(in[kp], shift_phasor(kp, lpad, 1.0f));
               } else {
-                // phases are given for the un-shifted frame: theta'[k] = theta[k] + 2 pi k lpad / n_fft
-                const float Sk = spec_to_mag<SRC>(__ldg(a.spec + row * kF + k), g);
-                const float Sp = spec_to_mag<SRC>(__ldg(a.spec + row * kF + kp), g);
-                float sk, ck, sp, cp;
-                if (a.angles != nullptr) {
-                  sincosf(__ldg(a.angles + row * kF + k), &sk, &ck);
-                  sincosf(__ldg(a.angles + row * kF + kp), &sp, &cp);
-                } else {
-                  sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + k)), &sk, &ck);
-                  sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + kp)), &sp, &cp);
+                // SYNTH: Y given directly (complex input, or magnitude with injected / generated phases), expressed in
+                // the shifted frame:  Y'[k] = Y[k] exp(+j 2 pi k lpad / n_fft)
+                float2 y[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int k = (e & 1) ? 1024 - (k0 + 32 * (e >> 1)) : k0 + 32 * (e >> 1);   // k0, 1024-k0, k0+32, 992-k0
+                  float2 val;
+                  if constexpr (SRC == SRC_COMPLEX) {
+                    val = (reinterpret_cast<const float2*>(a.cplx_in) + row * kF)[k];
+                  } else {
+                    const float S = spec_to_mag<SRC>(__ldg(a.spec + row * kF + k), g);
+                    float sn, cs;
+                    if (a.angles != nullptr) sincosf(__ldg(a.angles + row * kF + k), &sn, &cs);
+                    else sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + k)), &sn, &cs);
+                    val = make_float2(S * cs, S * sn);
+                  }
+                  y[e] = cmul(val, shift_phasor(k, lpad, 1.0f));
                 }
-                Yk = cmul(make_float2(Sk * ck, Sk * sk), shift_phasor(k, lpad, 1.0f));
-                Yp = cmul(make_float2(Sp * cp, Sp * sp), shift_phasor(kp, lpad, 1.0f));
+                if (m == 0 && l0) { y[0].y = 0.0f; y[1].y = 0.0f; }     // irfft ignores Im of DC / Nyquist
+                YkR = make_float2(y[0].x, y[2].x); YkI = make_float2(y[0].y, y[2].y);
+                YpR = make_float2(y[1].x, y[3].x); YpI = make_float2(y[1].y, y[3].y);
               }
-              if (MODE == MODE_SYNTH && l0 && k1 == 0) { Yk.y = 0.0f; Yp.y = 0.0f; }   // irfft ignores Im of DC / Nyquist
               // Z'2[k] = P + Q, Z'2[1024-k] = conj(P - Q),  P = Y[k] + conj(Y[1024-k]),  Q = conj(G_k) (Y[k] - conj(Y[1024-k]))
-              const float2 G = gt[k];
-              const float2 P = make_float2(Yk.x + Yp.x, Yk.y - Yp.y);
-              const float2 D = make_float2(Yk.x - Yp.x, Yk.y + Yp.y);
-              const float2 Q = make_float2(G.x * D.x + G.y * D.y, G.x * D.y - G.y * D.x);
-              v[k1] = make_float2(P.x + Q.x, -(P.y + Q.y));       // conj(Z'2[k])
-              snd[k1] = make_float2(P.x - Q.x, P.y - Q.y);        // conj(Z'2[1024-k])
-            }
-            if (l0) {   // k = 512 (self-paired): X = conj(Z[512]), Z'2 = 2 conj(Y), conj(Z'2) = 2 Y
+              const float2 PR = __fadd2_rn(YkR, YpR), PI = __fadd2_rn(YkI, neg2(YpI));
+              const float2 DR = __fadd2_rn(YkR, neg2(YpR)), DI = __fadd2_rn(YkI, YpI);
+              float2 vR = __ffma2_rn(GX, DR, PR);                  // Re(P + Q),  Re Q = GX DR + GY DI
+              vR = __ffma2_rn(GY, DI, vR);
+              float2 vI = __ffma2_rn(neg2(GX), DI, neg2(PI));      // -Im(P + Q), Im Q = GX DI - GY DR
+              vI = __ffma2_rn(GY, DR, vI);
+              R[m] = vR; I[m] = vI;                                // conj(Z'2[k])
+              SR[m] = __ffma2_rn(PR, splat(2.0f), neg2(vR));       // conj(Z'2[1024-k]) = P - Q
+              SI[m] = __ffma2_rn(PI, splat(2.0f), vI);
+            });
+            if (l0) {   // k = 512 (self-paired, register 16 = R[8].x): X = conj(Z[512]), Z'2 = 2 conj(Y), conj(Z'2) = 2 Y
               float2 Y;
               if constexpr (MODE == MODE_GL_ITER) {
                 const float S5 = spec_to_mag<SRC>(srow[512], g);
-                const float2 X = make_float2(v[16].x, -v[16].y);
+                const float2 X = make_float2(R[8].x, -I[8].x);
                 const float m = X.x * X.x + X.y * X.y;
-                const float im = rsqrtf(fmaxf(m, 1e-37f));
+                const float im = rsqrt_fast(fmaxf(m, kTiny));
                 const float f = S5 * im;
-                Y = make_float2(m > 1e-37f ? X.x * f : S5, X.y * f);
+                Y = make_float2(m > kTiny ? X.x * f : S5, X.y * f);
                 if (SC && own) {
                   const float d = m * im - S5;         // |X| = |Z[512]| (no factor 2 here)
                   sc_num += d * d;
@@ -370,43 +408,58 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               }
               z512 = make_float2(2.0f * Y.x, 2.0f * Y.y);
             }
-            // hand the partner its half of each pair
-#pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) {
-              r[k1].x = __shfl_sync(0xffffffffu, snd[k1].x, partner);
-              r[k1].y = __shfl_sync(0xffffffffu, snd[k1].y, partner);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 from_other = r[15 - i];                             // own register 31 - k1
-              const float2 from_self = i == 0 ? z512 : r[16 - i];              // lane 0: own register 32 - k1
-              v[16 + i] = l0 ? from_self : from_other;
-            }
+            // hand the partner its half of each pair: received r[k1] goes to own register 31 - k1 (lane 0: 32 - k1)
+            float rr_[16], ri_[16];
+            static_for<0, 8>([&](auto mc) {
+              constexpr int m = decltype(mc)::value;
+              rr_[2 * m] = __shfl_sync(0xffffffffu, SR[m].x, partner);
+              rr_[2 * m + 1] = __shfl_sync(0xffffffffu, SR[m].y, partner);
+              ri_[2 * m] = __shfl_sync(0xffffffffu, SI[m].x, partner);
+              ri_[2 * m + 1] = __shfl_sync(0xffffffffu, SI[m].y, partner);
+            });
+            static_for<0, 8>([&](auto jc) {
+              constexpr int j = decltype(jc)::value;       // registers 16 + 2j, 17 + 2j
+              const float ar = (j == 0) ? z512.x : rr_[(16 - 2 * j) & 15], ai = (j == 0) ? z512.y : ri_[(16 - 2 * j) & 15];
+              R[8 + j] = make_float2(l0 ? ar : rr_[15 - 2 * j], l0 ? rr_[15 - 2 * j] : rr_[14 - 2 * j]);
+              I[8 + j] = make_float2(l0 ? ai : ri_[15 - 2 * j], l0 ? ri_[15 - 2 * j] : ri_[14 - 2 * j]);
+            });
           }
 
           // ------------------------------------------------------------------ 1024-point transform, 32 x 32
-          // v[n2] = z[lane + 32 n2]  ->  v[k1] = Z[32 k1 + lane]
+          // element n2 = z[lane + 32 n2]  ->  element k1 = Z[32 k1 + lane]
 #pragma unroll 1
           for (int pass = 0; pass < 2; ++pass) {
-            fft32<false, 32>(v);
+            fft32p(R, I);
             if (pass == 0) {
 #pragma unroll
-              for (int k2 = 1; k2 < 32; ++k2) v[k2] = cmul(v[k2], tw[k2 * 32 + lane]);     // W_1024^(lane * k2)
+              for (int m = 0; m < 16; ++m) {                      // times W_1024^(lane * k2), k2 = 2m, 2m+1
+                const float4 w = tw4[m * 32 + lane];
+                const float2 WR = make_float2(w.x, w.y), WI = make_float2(w.z, w.w);
+                const float2 nr = __ffma2_rn(R[m], WR, neg2(__fmul2_rn(I[m], WI)));
+                I[m] = __ffma2_rn(R[m], WI, __fmul2_rn(I[m], WR));
+                R[m] = nr;
+              }
               __syncwarp();
 #pragma unroll
-              for (int k2 = 0; k2 < 32; ++k2) buf[k2 * kRowStride + lane] = v[k2];
+              for (int m = 0; m < 16; ++m) {                      // row k2: [re 0..31 | im 0..31], column = lane
+                buf[(2 * m) * kRowFloats + lane] = R[m].x;
+                buf[(2 * m) * kRowFloats + 32 + lane] = I[m].x;
+                buf[(2 * m + 1) * kRowFloats + lane] = R[m].y;
+                buf[(2 * m + 1) * kRowFloats + 32 + lane] = I[m].y;
+              }
               __syncwarp();
 #pragma unroll
-              for (int n1 = 0; n1 < 32; n1 += 2) {
-                const float4 q = *reinterpret_cast<const float4*>(&buf[lane * kRowStride + n1]);
-                v[n1] = make_float2(q.x, q.y);
-                v[n1 + 1] = make_float2(q.z, q.w);
+              for (int jq = 0; jq < 8; ++jq) {                    // row `lane`: elements n1 = 4 jq .. 4 jq + 3
+                const float4 qr = *reinterpret_cast<const float4*>(&buf[lane * kRowFloats + 4 * jq]);
+                const float4 qi = *reinterpret_cast<const float4*>(&buf[lane * kRowFloats + 32 + 4 * jq]);
+                R[2 * jq] = make_float2(qr.x, qr.y); R[2 * jq + 1] = make_float2(qr.z, qr.w);
+                I[2 * jq] = make_float2(qi.x, qi.y); I[2 * jq + 1] = make_float2(qi.z, qi.w);
               }
               if (MODE == MODE_GL_ITER && half == 0) {
                 // the exchange buffer is idle until the inverse transform: stream this frame's |S| row into it now,
                 // so that the HBM latency hides behind the second pass
                 __syncwarp();
-                s_off = row_to_smem_async(reinterpret_cast<float*>(buf), a.spec + row * kF, a.spec, a.spec_end, lane);
+                s_off = row_to_smem_async(buf, a.spec + row * kF, a.spec, a.spec_end, lane);
               }
             }
           }
@@ -415,37 +468,44 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         if constexpr (MODE == MODE_ANALYSIS) {
           // ---------------------------------------------------------------- spectrum out
           // X[k] = (E2 + G_k D2)/2, X[1024-k] = conj(E2 - G_k D2)/2 ; undo the circular shift for complex output
-          const int partner = (32 - lane) & 31;
-          const bool l0 = lane == 0;
-          const int lpad = (kNfft - g.win) >> 1;
-          float* magbuf = reinterpret_cast<float*>(buf);
+          float* magbuf = buf;
           float2* cout = reinterpret_cast<float2*>(a.cplx_out) + row * kF;
           __syncwarp();
-#pragma unroll
-          for (int k1 = 0; k1 < 16; ++k1) {
-            const float2 sv = l0 ? v[(32 - k1) & 31] : v[31 - k1];
-            float2 B;
-            B.x = __shfl_sync(0xffffffffu, sv.x, partner);
-            B.y = __shfl_sync(0xffffffffu, sv.y, partner);
-            const int k = 32 * k1 + lane, kp = 1024 - k;
-            const float2 A = v[k1];
-            const float2 E2 = make_float2(A.x + B.x, A.y - B.y);
-            const float2 D2 = make_float2(A.x - B.x, A.y + B.y);
-            const float2 Tt = cmul(gt[k], D2);
-            float2 Xk = make_float2(0.5f * (E2.x + Tt.x), 0.5f * (E2.y + Tt.y));
-            float2 Xp = make_float2(0.5f * (E2.x - Tt.x), -0.5f * (E2.y - Tt.y));
-            if (l0 && k1 == 0) { Xk.y = 0.0f; Xp.y = 0.0f; }
+          static_for<0, 8>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            constexpr int ms = (m == 0) ? 0 : 16 - m;
+            const float s0r = l0 ? R[ms].x : R[15 - m].y, s0i = l0 ? I[ms].x : I[15 - m].y;
+            const float s1r = l0 ? R[15 - m].y : R[15 - m].x, s1i = l0 ? I[15 - m].y : I[15 - m].x;
+            const float2 BR = shfl2(s0r, s1r, partner), BI = shfl2(s0i, s1i, partner);
+            const int k0 = 64 * m + lane;
+            const float4 gq = g4[m * 32 + lane];
+            const float2 GX = make_float2(gq.x, gq.y), GY = make_float2(gq.z, gq.w);
+            const float2 E2R = __fadd2_rn(R[m], BR), E2I = __fadd2_rn(I[m], neg2(BI));
+            const float2 D2R = __fadd2_rn(R[m], neg2(BR)), D2I = __fadd2_rn(I[m], BI);
+            float2 XkR = __ffma2_rn(GX, D2R, E2R);
+            XkR = __ffma2_rn(neg2(GY), D2I, XkR);
+            float2 XkI = __ffma2_rn(GX, D2I, E2I);
+            XkI = __ffma2_rn(GY, D2R, XkI);
+            float2 XpR = __ffma2_rn(E2R, splat(2.0f), neg2(XkR));
+            float2 XpI = __ffma2_rn(E2I, splat(-2.0f), XkI);
+            XkR = __fmul2_rn(XkR, splat(0.5f)); XkI = __fmul2_rn(XkI, splat(0.5f));
+            XpR = __fmul2_rn(XpR, splat(0.5f)); XpI = __fmul2_rn(XpI, splat(0.5f));
+            if (m == 0 && l0) { XkI.x = 0.0f; XpI.x = 0.0f; }
             if constexpr (SRC == OUT_COMPLEX) {
               // frame tap m sits at transform sample lpad + m: X_true[k] = X[k] * exp(-j 2 pi k lpad / n_fft)
-              cout[k] = cmul(Xk, shift_phasor(k, lpad, -1.0f));
-              cout[kp] = cmul(Xp, shift_phasor(kp, lpad, -1.0f));
+              cout[k0] = cmul(make_float2(XkR.x, XkI.x), shift_phasor(k0, lpad, -1.0f));
+              cout[k0 + 32] = cmul(make_float2(XkR.y, XkI.y), shift_phasor(k0 + 32, lpad, -1.0f));
+              cout[1024 - k0] = cmul(make_float2(XpR.x, XpI.x), shift_phasor(1024 - k0, lpad, -1.0f));
+              cout[992 - k0] = cmul(make_float2(XpR.y, XpI.y), shift_phasor(992 - k0, lpad, -1.0f));
             } else {
-              magbuf[k] = sqrtf(Xk.x * Xk.x + Xk.y * Xk.y);
-              magbuf[kp] = sqrtf(Xp.x * Xp.x + Xp.y * Xp.y);
+              magbuf[k0] = sqrtf(XkR.x * XkR.x + XkI.x * XkI.x);
+              magbuf[k0 + 32] = sqrtf(XkR.y * XkR.y + XkI.y * XkI.y);
+              magbuf[1024 - k0] = sqrtf(XpR.x * XpR.x + XpI.x * XpI.x);
+              magbuf[992 - k0] = sqrtf(XpR.y * XpR.y + XpI.y * XpI.y);
             }
-          }
+          });
           if (l0) {   // k = 512: X = conj(Z[512])
-            const float2 Xc = make_float2(v[16].x, -v[16].y);
+            const float2 Xc = make_float2(R[8].x, -I[8].x);
             if constexpr (SRC == OUT_COMPLEX) cout[512] = cmul(Xc, shift_phasor(512, lpad, -1.0f));
             else magbuf[512] = sqrtf(Xc.x * Xc.x + Xc.y * Xc.y);
           }
@@ -467,20 +527,17 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
             }
           }
         } else {
-          // ---------------------------------------------------------------- window -> the warp's overlap-add slot
-          // v[n2] = conj(z'[lane + 32 n2]):  y[2q] = Re, y[2q+1] = -Im
+          // ---------------------------------------------------------------- the warp's overlap-add slot
+          // element n2 = conj(z'[lane + 32 n2]):  sample 2q = Re, sample 2q+1 = -Im  (q = lane + 32 n2); the slot keeps
+          // the even samples and the (un-negated) odd samples in two planes; window and sign are applied in the
+          // overlap-add
           __syncwarp();                       // all lanes done reading the exchange buffer: it becomes the slot
-          float* slot = reinterpret_cast<float*>(buf);
 #pragma unroll
-          for (int n2 = 0; n2 < 32; ++n2) {
-            const int q = lane + 32 * n2;
-            if (n2 < NZ) {
-              if (q < g.half)
-                *reinterpret_cast<float2*>(slot + 2 * q) = make_float2(v[n2].x * wE[q], -v[n2].y * wO[q]);
-              else if (kStd && 2 * q < ND * g.hop)
-                *reinterpret_cast<float2*>(slot + 2 * q) = make_float2(0.0f, 0.0f);      // zero padding up to 5*hop
-            } else if (kStd && 2 * q < ND * g.hop) {
-              *reinterpret_cast<float2*>(slot + 2 * q) = make_float2(0.0f, 0.0f);
+          for (int m = 0; m < 16; ++m) {
+            if (2 * m < NZ) {
+              const int q = lane + 64 * m;
+              if (q < g.half) { buf[q] = R[m].x; buf[kSlotPlane + q] = I[m].x; }
+              if (q + 32 < g.half) { buf[q + 32] = R[m].y; buf[kSlotPlane + q + 32] = I[m].y; }
             }
           }
         }
@@ -493,31 +550,43 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
       }
 
       if constexpr (MODE != MODE_ANALYSIS) {
-        // -------------------------------------------------------------------- overlap-add + 1/(N wss) + store
+        // -------------------------------------------------------------------- overlap-add + window + 1/(N wss) + store
         // each thread owns a residue rr (mod hop): acc[j] is span sample j*hop + rr; frame f adds its taps
-        // rr + d*hop (d < ND) to acc[f + d].  All register indices are static; lanes read consecutive addresses.
-        // The carry (samples that later frames still add to) is read and re-written by the same thread.
+        // rr + d*hop (d < ND), weighted by the synthesis window, to acc[f + d].  All register indices are static;
+        // lanes read consecutive addresses of alternating slot planes.  The carry (samples that later frames still
+        // add to) is read and re-written by the same thread.
         const int fv_lo = first_needed > t0 ? first_needed - t0 : 0;
         const int fv_hi = (T - t0) < kNF ? (T - t0) : kNF;
         // the utterance's last tile also flushes what would be its carry (samples up to hop*(T-1) end there)
         const int out_len = (t0 + kNF >= T) ? g.span_len : kNF * g.hop;
         float* __restrict__ dst = a.wav_out + woff;
-        const bool interior = kStd && write_out && fv_lo == 0 && fv_hi == kNF && i0 >= 0 && t0 + kNF < T &&
+        const bool interior = write_out && fv_lo == 0 && fv_hi == kNF && i0 >= 0 && t0 + kNF < T &&
                               i0 + kNF * g.hop <= L && t0 >= ND - 1;
         for (int rr = tid; rr < g.hop; rr += kThreads) {
           float acc[kNF + ND - 1];
+          float wreg[ND];
+          int off[ND];
+#pragma unroll
+          for (int d = 0; d < ND; ++d) {
+            const int m = rr + d * g.hop;                 // window tap; odd taps carry the conjugation sign
+            const float w = m < g.win ? ((m & 1) ? -__ldg(tb.wO + (m >> 1)) : __ldg(tb.wE + (m >> 1))) : 0.0f;
+            wreg[d] = w;
+            off[d] = m < g.win ? ((m & 1) ? kSlotPlane : 0) + (m >> 1) : 0;
+          }
 #pragma unroll
           for (int j = 0; j < kNF + ND - 1; ++j) {
             const int sidx = j * g.hop + rr;
             acc[j] = (has_carry && j < ND - 1 && sidx < g.carry_len) ? carry[sidx] : 0.0f;
           }
-          if (interior) {
 #pragma unroll
-            for (int f = 0; f < kNF; ++f) {
-              const float* sl = smem + f * kBufFloats + rr;
+          for (int f = 0; f < kNF; ++f) {
+            if (interior || (f >= fv_lo && f < fv_hi)) {
+              const float* sl = smem + f * kBufFloats;
 #pragma unroll
-              for (int d = 0; d < ND; ++d) acc[f + d] += sl[d * g.hop];       // slots are zero padded to ND*hop
+              for (int d = 0; d < ND; ++d) acc[f + d] = fmaf(sl[off[d]], wreg[d], acc[f + d]);
             }
+          }
+          if (interior) {
             const float inv = pw[rr];
 #pragma unroll
             for (int j = 0; j < kNF; ++j) dst[i0 + j * g.hop + rr] = acc[j] * inv;
@@ -527,15 +596,6 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               if (c < g.carry_len) carry[c] = acc[j];
             }
           } else {
-#pragma unroll
-            for (int f = 0; f < kNF; ++f) {
-              if (f >= fv_lo && f < fv_hi) {
-                const float* sl = smem + f * kBufFloats + rr;
-#pragma unroll
-                for (int d = 0; d < ND; ++d)
-                  if (kStd || rr + d * g.hop < g.win) acc[f + d] += sl[d * g.hop];
-              }
-            }
             const int dmax = (g.win - 1 - rr) / g.hop;
 #pragma unroll 1
             for (int j = 0; j < kNF + ND - 1; ++j) {
@@ -553,7 +613,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
                     for (int d = 0, m = rr; m < g.win; ++d, m += g.hop) {
                       const int tt = t0 + j - d;
                       if (tt >= 0 && tt < T) {
-                        const float wv = (m & 1) ? wO[m >> 1] : wE[m >> 1];
+                        const float wv = (m & 1) ? __ldg(tb.wO + (m >> 1)) : __ldg(tb.wE + (m >> 1));
                         ws = fmaf(wv, wv, ws);
                       }
                     }

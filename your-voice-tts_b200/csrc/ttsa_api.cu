@@ -92,14 +92,22 @@ extern "C" uint64_t ttsa_launch_count(void) { return g_launches.load(); }
 // ---------------------------------------------------------------------------------------------------------
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+static int kernel_class(const ttsa_config& c) {
+  // class 20 ("standard"): <= 20 non-zero rows of packed input and <= 5 window taps per residue mod hop.
+  // True for every shipped geometry (275/1102, 200/800, 300/1200); class 32 covers the rest up to win <= 9*hop.
+  const int half = (c.win_length + 1) / 2;
+  return (half <= 20 * 32 && (c.win_length + c.hop_length - 1) / c.hop_length <= 5) ? 20 : 32;
+}
+
 static int build_geo(const ttsa_config& c, Geo& g) {
+  const int nz = kernel_class(c);
   std::memset(&g, 0, sizeof(g));
   g.hop = c.hop_length;
   g.win = c.win_length;
   const int lpad = (kNfft - c.win_length) / 2;
   g.off0 = kNfft / 2 - lpad;
   g.half = (c.win_length + 1) / 2;
-  g.wlen = round_up(g.half, 32);
+  g.wlen = nz * 32;
   g.carry_len = c.win_length - c.hop_length;
   g.span_len = (kNF - 1) * c.hop_length + c.win_length;
   g.nwarm = (c.win_length - 1) / c.hop_length;
@@ -108,13 +116,15 @@ static int build_geo(const ttsa_config& c, Geo& g) {
   g.preemph = (float)c.preemphasis;
   // shared memory layout
   int off = kNF * kBufFloats;
-  const int plane_len = (g.span_len + 1) / 2 + 1;
+  // a frame's loads start at up to ((kNF-1)*hop + 1)/2 and reach nz*32 packed samples further (zero tail)
+  const int plane_len = round_up(((kNF - 1) * c.hop_length + 1) / 2 + 1 + nz * 32, 32);
+  g.plane_len = plane_len;
   g.sm_plane0 = off;
-  off += round_up(plane_len, 32) + 16;          // plane1 starts 16 banks away from plane0
+  off += plane_len + 16;                        // plane1 starts 16 banks away from plane0
   g.sm_plane1 = off;
-  off += round_up(plane_len, 32);
+  off += plane_len;
   g.sm_carry0 = off; off += round_up(g.carry_len + 1, 4);
-  g.sm_carry1 = off; off += round_up(g.carry_len + 1, 4);
+  g.sm_carry1 = g.sm_carry0;
   g.sm_wE = off; off += g.wlen;
   g.sm_wO = off; off += g.wlen;
   g.sm_pw = off; off += round_up(g.hop, 4);
@@ -173,10 +183,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->cfg = c;
   p->device = device;
   build_geo(c, p->geo);
-  // kernel class 20 ("standard"): <= 20 non-zero rows of packed input, <= 5 taps per residue mod hop, and 5*hop floats
-  // fit the zero-padded overlap-add slot.  True for every shipped geometry (275/1102, 200/800, 300/1200).
-  p->nz = (p->geo.half <= 20 * 32 && (c.win_length + c.hop_length - 1) / c.hop_length <= 5 &&
-           5 * c.hop_length <= kBufFloats) ? 20 : 32;
+  p->nz = kernel_class(c);
   if ((size_t)p->geo.sm_total * 4 > 227 * 1024) {
     delete p;
     return fail(TTSA_ERR_UNSUPPORTED, "hop/win need %d bytes of shared memory per CTA", p->geo.sm_total * 4);
@@ -219,19 +226,31 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->num_sms = prop.multiProcessorCount;
 
   const std::vector<double> w = ttsa_host::hann_periodic(c.win_length);
-  std::vector<float> h_tw(2048), h_g(1024), h_wE(1024, 0.f), h_wO(1024, 0.f), h_pw(round_up(c.hop_length, 4), 1.f);
-  for (int a = 0; a < 32; ++a)
-    for (int b = 0; b < 32; ++b) {
-      const double ang = 2.0 * ttsa_host::kPi * ((a * b) % 1024) / 1024.0;
-      h_tw[2 * (a * 32 + b)] = (float)std::cos(ang);
-      h_tw[2 * (a * 32 + b) + 1] = (float)-std::sin(ang);
-    }
-  for (int k = 0; k < 512; ++k) {
-    const double ang = ttsa_host::kPi * k / 1024.0;
-    h_g[2 * k] = (float)-std::sin(ang);
-    h_g[2 * k + 1] = (float)-std::cos(ang);
-  }
+  std::vector<float> h_tw(2048), h_g(1024), h_wE(1024, 0.f), h_wO(1024, 0.f), h_wE2(1024, 0.f), h_wO2(1024, 0.f),
+      h_pw(round_up(c.hop_length, 4), 1.f);
+  for (int m = 0; m < 16; ++m)            // tw4[m][lane] = (wr(2m), wr(2m+1), wi(2m), wi(2m+1)), w(k) = W_1024^(lane k)
+    for (int lane = 0; lane < 32; ++lane)
+      for (int e = 0; e < 2; ++e) {
+        const double ang = 2.0 * ttsa_host::kPi * ((lane * (2 * m + e)) % 1024) / 1024.0;
+        h_tw[4 * (m * 32 + lane) + e] = (float)std::cos(ang);
+        h_tw[4 * (m * 32 + lane) + 2 + e] = (float)-std::sin(ang);
+      }
+  for (int m = 0; m < 8; ++m)             // g4[m][lane] = (gx(2m), gx(2m+1), gy(2m), gy(2m+1)), g(k1) = -j W_2048^(32 k1 + lane)
+    for (int lane = 0; lane < 32; ++lane)
+      for (int e = 0; e < 2; ++e) {
+        const double ang = ttsa_host::kPi * (32 * (2 * m + e) + lane) / 1024.0;
+        h_g[4 * (m * 32 + lane) + e] = (float)-std::sin(ang);
+        h_g[4 * (m * 32 + lane) + 2 + e] = (float)-std::cos(ang);
+      }
   for (int m = 0; m < c.win_length; ++m) ((m & 1) ? h_wO : h_wE)[m >> 1] = (float)w[m];
+  for (int m = 0; m < 16; ++m)            // paired taps for two packed rows: q = lane + 64 m and q + 32
+    for (int lane = 0; lane < 32; ++lane) {
+      const int q = lane + 64 * m;
+      h_wE2[2 * (m * 32 + lane)] = h_wE[q];
+      h_wE2[2 * (m * 32 + lane) + 1] = q + 32 < 1024 ? h_wE[q + 32] : 0.f;
+      h_wO2[2 * (m * 32 + lane)] = h_wO[q];
+      h_wO2[2 * (m * 32 + lane) + 1] = q + 32 < 1024 ? h_wO[q + 32] : 0.f;
+    }
   for (int r = 0; r < c.hop_length; ++r) {
     double acc = 0.0;
     for (int m = r; m < c.win_length; m += c.hop_length) { const double wf = (double)(float)w[m]; acc += wf * wf; }
@@ -260,7 +279,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   std::vector<Piece> pieces = {
       {h_tw.data(), h_tw.size() * 4, 0}, {h_g.data(), h_g.size() * 4, 0}, {h_wE.data(), h_wE.size() * 4, 0},
       {h_wO.data(), h_wO.size() * 4, 0}, {h_pw.data(), h_pw.size() * 4, 0}, {h_lo.data(), h_lo.size() * 4, 0},
-      {h_cnt.data(), h_cnt.size() * 4, 0}, {h_val.data(), h_val.size() * 4, 0}, {h_pinvT.data(), h_pinvT.size() * 4, 0}};
+      {h_cnt.data(), h_cnt.size() * 4, 0}, {h_val.data(), h_val.size() * 4, 0}, {h_pinvT.data(), h_pinvT.size() * 4, 0},
+      {h_wE2.data(), h_wE2.size() * 4, 0}, {h_wO2.data(), h_wO2.size() * 4, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -272,8 +292,10 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
   }
   char* base = (char*)p->d_block;
-  p->tb.tw = (const float2*)(base + pieces[0].off);
-  p->tb.g = (const float2*)(base + pieces[1].off);
+  p->tb.tw4 = (const float4*)(base + pieces[0].off);
+  p->tb.g4 = (const float4*)(base + pieces[1].off);
+  p->tb.wE2 = (const float2*)(base + pieces[9].off);
+  p->tb.wO2 = (const float2*)(base + pieces[10].off);
   p->tb.wE = (const float*)(base + pieces[2].off);
   p->tb.wO = (const float*)(base + pieces[3].off);
   p->tb.pw = (const float*)(base + pieces[4].off);
