@@ -6,12 +6,12 @@ def find(s):
     return next(i+1 for i,l in enumerate(lines) if s in l)
 marks=[('setup',0),('stage helpers',find('span staging helpers')),('tile loop/stage',find('previous segment is done with planes')),('frame load',find('window the frame')),
        ('middle',find('per-bin step -> conj')),('shfl2',find('hand the partner its half')),('transform glue',find('1024-point transform, 32 x 32')),('analysis out',find('spectrum out')),
-       ('slot store',find("window -> the warp's overlap-add slot")),('post-frame sync/stage_load',find('slots complete; planes consumed')),('OLA',find('overlap-add + 1/(N wss) + store')),('stage_store/sync',find('if (have_next) stage_store')),('sc',find('if constexpr (MODE == MODE_GL_ITER && SC)'))]
+       ('slot store',find("the warp's overlap-add slot")),('post-frame sync/stage_load',find('slots complete; planes consumed')),('OLA',find('overlap-add + window + 1/(N wss) + store')),('stage_store/sync',find('if (have_next) stage_store')),('sc',find('if constexpr (MODE == MODE_GL_ITER && SC)'))]
 helper_end=find('// the kernel')
 def region(l):
     if l is None: return 'none'
     f,n=l
-    if f=='fft32.cuh': return 'fft32'
+    if f in ('fft32.cuh','fft32p.cuh'): return 'fft32'
     if f!='frame_kernels.cuh': return f
     if n<helper_end: return 'passes(twiddle/exchange/cp.async)'
     r='setup'

@@ -37,6 +37,7 @@ struct FrameArgs {
   const float* angles;    // [sum_T, F]      SYNTH: initial phases in radians, or nullptr -> counter RNG
   const float* cplx_in;   // [sum_T, F, 2]   SYNTH with SRC_COMPLEX
   const float* wav_in;    // packed wav      GL_ITER (previous y) / ANALYSIS
+  const float* wav_end;   // one past the last float of wav_in (bounds for 16-byte span copies)
   float* wav_out;         // packed wav      GL_ITER / SYNTH
   float* cplx_out;        // [sum_T, F, 2]   ANALYSIS OUT_COMPLEX
   float* lin_out;         // [sum_T, F]      ANALYSIS OUT_FEATURES (nullable)

@@ -18,6 +18,11 @@ const char* configure_gl(size_t smem_bytes, int* ctas_per_sm);
 const char* configure_synth(size_t smem_bytes);
 const char* configure_analysis(size_t smem_bytes);
 const char* launch_gl(int src, int nz, bool sc, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
+// barrier-free warp-chain Griffin-Lim iteration (standard geometry class); smem layout in gl_chain.cuh
+struct ChainSmem;
+const char* configure_gl_chain(size_t smem_bytes, int* ctas_per_sm);
+const char* launch_gl_chain(int src, bool sc, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&,
+                            const FrameArgs&, const ChainSmem&, long long total_frames);
 const char* launch_synth(int src, int nz, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 const char* launch_analysis(int out, int nz, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 

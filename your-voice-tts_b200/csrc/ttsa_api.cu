@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -11,6 +12,7 @@
 #include "../../include/ttsa.h"
 #include "aux_kernels.cuh"
 #include "frame_launch.cuh"
+#include "gl_chain.cuh"
 #include "host_tables.hpp"
 
 using namespace ttsa;
@@ -61,6 +63,9 @@ struct ttsa_plan {
   std::vector<double> h_inv_mel;   // [F][num_mels]
   int nz = 32;                     // compile-time zero-pruning class of the frame kernels (20 or 32)
   int ctas_per_sm = 1;
+  bool use_chain = false;          // Griffin-Lim iterations run the barrier-free warp-chain kernel (standard class)
+  ChainSmem chain_sm;
+  int chain_ctas_per_sm = 1;
   // device allocations
   void* d_block = nullptr;         // one allocation holding every table
   const float* d_pinvT = nullptr;  // [num_mels][ldp]
@@ -311,6 +316,25 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   const char* err = configure_frame_kernels(smem_bytes, &occ);
   if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
   p->ctas_per_sm = occ < 1 ? 1 : occ;
+  if (p->nz == 20 && c.win_length + (kNF - 1) * c.hop_length <= kAccLen) {
+    ChainSmem& cs = p->chain_sm;
+    int off = kNF * kBufFloats;
+    cs.acc = off; off += 2 * kAccPlane;
+    cs.wE = off; off += 20 * 32;
+    cs.wO = off; off += 20 * 32;
+    cs.pw = off; off += round_up(c.hop_length, 4);
+    cs.tw = off; off += 2048;
+    cs.g = off; off += 1024;
+    cs.total = off;
+    int occ2 = 0;
+    err = configure_gl_chain((size_t)cs.total * 4, &occ2);
+    if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "chain kernel configuration: %s", err); }
+    p->chain_ctas_per_sm = occ2 < 1 ? 1 : occ2;
+    // Experimental: measured slower than the tiled kernel on B200 (0.23 vs 0.20 ms per iteration at 64 x 482 frames:
+    // the strictly ordered adds convoy).  Opt in with TTSA_GL_KERNEL=chain for profiling.
+    const char* sel = std::getenv("TTSA_GL_KERNEL");
+    p->use_chain = sel != nullptr && std::strcmp(sel, "chain") == 0;
+  }
   cudaError_t e = cudaFuncSetAttribute(mel_to_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMtlMaxK * (kMtlBins + kMtlRows) * 4);
   if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "mel kernel configuration: %s", cudaGetErrorString(e)); }
@@ -573,8 +597,18 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
     FrameArgs b{};
     b.spec = spec_dev; b.spec_end = spec_dev + (size_t)batch->total_frames * kF;
     b.wav_in = bufs[(i - 1) & 1]; b.wav_out = bufs[i & 1];
+    b.wav_end = b.wav_in + batch->total_samples;
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
-    if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st)) return rc;
+    if (plan->use_chain) {
+      const long long want = (batch->total_frames + kNF - 1) / kNF;
+      const long long max_ctas = (long long)plan->chain_ctas_per_sm * plan->num_sms;
+      const int grid = (int)std::max<long long>(1, std::min(want, max_ctas));
+      const char* err = launch_gl_chain(spec_kind, sc_log_dev != nullptr, grid, (size_t)plan->chain_sm.total * 4, st, plan->geo,
+                                        plan->tb, batch->dev, b, plan->chain_sm, batch->total_frames);
+      if (err) return fail(TTSA_ERR_CUDA, "Griffin-Lim chain kernel launch: %s", err);
+    } else if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st)) {
+      return rc;
+    }
   }
   if (bufs[iters & 1] != last) return fail(TTSA_ERR_CUDA, "internal: buffer rotation");
   if (deemph) return deemph_launch(plan, batch, last, wav_out_dev, agg, st);
