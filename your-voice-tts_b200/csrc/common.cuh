@@ -27,7 +27,7 @@ struct Geo {
   int num_mels;
   float inv_hop;
   // shared memory layout (float offsets)
-  int sm_plane0, sm_plane1, sm_carry0, sm_carry1, sm_wE, sm_wO, sm_pw, sm_tw, sm_g, sm_total;
+  int sm_plane0, sm_plane1, sm_carry0, sm_carry1, sm_wE, sm_wO, sm_pw, sm_wsyn, sm_tw, sm_g, sm_total;
   // spectrogram value -> magnitude:  S = exp2(c1 * clip(x, lo, hi) + c0)   (denormalize, +ref, db_to_amp, **power fused)
   float s_c1, s_c0, s_lo, s_hi;
   // amplitude -> normalised dB:      v = clip(n_a * log2(max(min_amp, a)) + n_b, n_lo, n_hi)

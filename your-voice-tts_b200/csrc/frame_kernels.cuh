@@ -84,6 +84,10 @@ __device__ __forceinline__ int row_to_smem_async(float* dst, const float* row_pt
   const int off = (int)((reinterpret_cast<unsigned long long>(row_ptr) >> 2) & 3ull);
   const float* base = row_ptr - off;                      // 16-byte aligned
   const int nchunks = (off + kF + 3) >> 2;
+  if (base >= lo && base + 4 * nchunks <= hi) {           // every chunk inside the tensor (all rows but the last)
+    for (int c = lane; c < nchunks; c += 32) cp_async16(dst + 4 * c, base + 4 * c);
+    return off;
+  }
   for (int c = lane; c < nchunks; c += 32) {
     const float* gsrc = base + 4 * c;
     if (gsrc >= lo && gsrc + 4 <= hi) {
@@ -154,6 +158,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
   const float2* const wE2 = reinterpret_cast<const float2*>(smem + g.sm_wE);
   const float2* const wO2 = reinterpret_cast<const float2*>(smem + g.sm_wO);
   float* const pw = smem + g.sm_pw;
+  float* const wsyn = smem + g.sm_wsyn;         // synthesis window per tap, odd taps negated (conjugate-FFT inverse)
   const float4* const tw4 = reinterpret_cast<const float4*>(smem + g.sm_tw);
   const float4* const g4 = reinterpret_cast<const float4*>(smem + g.sm_g);
 
@@ -165,8 +170,10 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     reinterpret_cast<float2*>(smem + g.sm_wO)[i] = tb.wO2[i];
   }
   for (int i = tid; i < g.plane_len; i += kThreads) { plane0[i] = 0.0f; plane1[i] = 0.0f; }
-  if constexpr (MODE != MODE_ANALYSIS)
+  if constexpr (MODE != MODE_ANALYSIS) {
     for (int i = tid; i < g.hop; i += kThreads) pw[i] = tb.pw[i] * kInvN;     // 1/wss and the 1/n_fft of the inverse FFT
+    for (int i = tid; i < g.win; i += kThreads) wsyn[i] = (i & 1) ? -tb.wO[i >> 1] : tb.wE[i >> 1];
+  }
 
   // contiguous tile range of this CTA over the flattened (utterance, tile) list
   const long long tile_lo = (long long)blockIdx.x * bd.total_tiles / gridDim.x;
@@ -235,11 +242,10 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
       }
     };
     auto stage_store = [&](int jt) {
+      float* const pl = ((tid & 1) ? plane1 : plane0) + (tid >> 1);    // parity of tid + e*kThreads = parity of tid
 #pragma unroll
-      for (int e = 0; e < kStage; ++e) {
-        const int s = tid + e * kThreads;
-        if (s < g.span_len) ((s & 1) ? plane1 : plane0)[s >> 1] = stg[e];
-      }
+      for (int e = 0; e < kStage; ++e)
+        if (tid + e * kThreads < g.span_len) pl[e * (kThreads / 2)] = stg[e];
       const int i0 = jt * kNF * g.hop - g.off0;
       for (int s = tid + kStage * kThreads; s < g.span_len; s += kThreads) {     // spans longer than the register window
         const int j = reflect_index(i0 + s, L);
@@ -570,8 +576,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
 #pragma unroll
           for (int d = 0; d < ND; ++d) {
             const int m = rr + d * g.hop;                 // window tap; odd taps carry the conjugation sign
-            const float w = m < g.win ? ((m & 1) ? -__ldg(tb.wO + (m >> 1)) : __ldg(tb.wE + (m >> 1))) : 0.0f;
-            wreg[d] = w;
+            wreg[d] = m < g.win ? wsyn[m] : 0.0f;
             off[d] = m < g.win ? ((m & 1) ? kSlotPlane : 0) + (m >> 1) : 0;
           }
 #pragma unroll

@@ -133,6 +133,7 @@ static int build_geo(const ttsa_config& c, Geo& g) {
   g.sm_wE = off; off += g.wlen;
   g.sm_wO = off; off += g.wlen;
   g.sm_pw = off; off += round_up(g.hop, 4);
+  g.sm_wsyn = off; off += round_up(g.win, 4);
   g.sm_tw = off; off += 2048;
   g.sm_g = off; off += 1024;
   g.sm_total = off;
