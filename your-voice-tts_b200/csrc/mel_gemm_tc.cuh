@@ -1,0 +1,225 @@
+// mel <-> linear as a tensor-core GEMM (tcgen05.mma, accumulator in TMEM) with fp32-equivalent precision.
+//
+//   _mel_to_linear   lin[row, k] = max(1e-10, sum_m pinv[k, m] amp[row, m])      utils/audio.py:64-66
+//   _linear_to_mel   mel[row, m] = sum_k basis[m, k] amp[row, k]                 utils/audio.py:60-62
+//
+// Both are D[rows x N] = A[rows x K] * B[N x K]^T with a plan-constant B (pseudo-inverse: N = 1025, K = 80; mel basis:
+// N = 80, K = 1025).  A single-pass TF32/BF16 product fails the 60 dB Griffin-Lim bar on the sign-cancelling
+// pseudo-inverse (SURVEY: 40 dB), so each fp32 operand is split into three bf16 terms (hi + mid + lo = 24 mantissa
+// bits) and the six products hi*hi, hi*mid, mid*hi, hi*lo, mid*mid, lo*hi are accumulated in fp32 in tensor memory:
+// 6 x (K/16) UMMA instructions of shape 128 x N x 16 per tile.
+//
+// CTA = 256 threads, one 128-row tile of A, one N-tile of B, K walked in chunks of 80.  Per chunk: A is converted
+// (prologue: denormalise + dB->amplitude when the input is a normalised spectrogram), split and written to shared
+// memory in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices); B was pre-split and
+// pre-arranged in that layout at plan creation and is copied verbatim.  One elected thread issues the MMAs and commits
+// them to an mbarrier.  Epilogue: tcgen05.ld (one TMEM lane = one output row per thread), clamp / power / dB, staged
+// through shared memory for coalesced row-major stores.
+#pragma once
+#include <cuda_bf16.h>
+#include "aux_kernels.cuh"
+
+namespace ttsa {
+
+constexpr int kTcRows = 128;        // UMMA M
+constexpr int kTcChunk = 80;        // K per chunk (5 UMMA K-steps of 16 bf16)
+constexpr int kTcKSteps = kTcChunk / 16;
+constexpr int kTcThreads = 256;     // 8 warps: warps w and w + 4 share TMEM lanes 32 (w % 4) .. + 31 and split the columns
+
+struct TcGemmParams {
+  MelParams mp;
+  const float* a;            // [rows, lda] fp32
+  int lda;                   // elements per A row (80 or 1025)
+  int k_total;               // valid K (A columns); chunks beyond are zero padded
+  int n_chunks;
+  const __nv_bfloat16* b;    // canonical pre-split B: [n_tile][chunk][part 3][kb 10][rg N/8][8][8]
+  float* out;                // [rows, ldo]
+  int ldo;                   // 1025 or num_mels
+  int n_valid;               // valid output columns (1025 or num_mels)
+  int in_kind, out_kind;
+  int mode;                  // 0 = mel_to_linear epilogue (max 1e-10, optional power), 1 = linear_to_mel (optional norm dB)
+};
+
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // K-major, SWIZZLE_NONE: start address, leading (K) byte offset, stride (M/N) byte offset in 16-byte units; version 1
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int N_TILE>   // UMMA N (multiple of 16, <= 256)
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_tc_kernel(const TcGemmParams p) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  constexpr int kTmemCols = N_TILE <= 32 ? 32 : N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
+  constexpr uint32_t kABytes = kTcRows * kTcChunk * 2;        // one bf16 part of the A chunk
+  constexpr uint32_t kBBytes = N_TILE * kTcChunk * 2;         // one bf16 part of the B chunk
+  constexpr uint32_t kLboA = (kTcRows / 8) * 128;             // byte stride between 8-element K blocks
+  constexpr uint32_t kLboB = (N_TILE / 8) * 128;
+  constexpr int kStageLd = N_TILE + 1;
+  // instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+
+  unsigned char* const smA = tc_smem;                          // 3 parts
+  unsigned char* const smB = tc_smem + 3 * kABytes;            // 3 parts
+  float* const stage = reinterpret_cast<float*>(tc_smem);      // epilogue staging (operands are dead by then)
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long row0 = (long long)blockIdx.x * kTcRows;
+  const int n_tile = blockIdx.y;
+
+  if (warp == 0) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar);
+  const uint32_t smA_addr = (uint32_t)__cvta_generic_to_shared(smA);
+  const uint32_t smB_addr = (uint32_t)__cvta_generic_to_shared(smB);
+
+  for (int ch = 0; ch < p.n_chunks; ++ch) {
+    if (ch > 0) {
+      // the previous chunk's MMAs must have consumed shared memory before it is overwritten
+      const uint32_t parity = (uint32_t)((ch - 1) & 1);
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, q;\n\t}\n"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // ---- A chunk: fp32 -> amplitude -> three bf16 terms, canonical layout
+    const int k0 = ch * kTcChunk;
+    for (int e = tid; e < kTcRows * kTcChunk; e += kTcThreads) {
+      const int r = e / kTcChunk, kk = e - r * kTcChunk;
+      const long long row = row0 + r;
+      const int k = k0 + kk;
+      float x = 0.0f;
+      if (row < p.mp.rows && k < p.k_total) {
+        x = mel_in_value(__ldg(p.a + row * p.lda + k), p.in_kind, p.mp);
+        if (p.mode == 1 && p.in_kind == 1) x = fabsf(x);       // out_linear_to_mel takes np.abs (utils/audio.py:177)
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      const float r1 = x - __bfloat162float(h);
+      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+      const uint32_t off = (uint32_t)(kk >> 3) * kLboA + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(kk & 7) * 2u;
+      *reinterpret_cast<__nv_bfloat16*>(smA + off) = h;
+      *reinterpret_cast<__nv_bfloat16*>(smA + kABytes + off) = m;
+      *reinterpret_cast<__nv_bfloat16*>(smA + 2 * kABytes + off) = l;
+    }
+    // ---- B chunk: already split and laid out; verbatim 16-byte copies
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(p.b) + ((size_t)n_tile * p.n_chunks + ch) * (3 * kBBytes / 16);
+      uint4* dst = reinterpret_cast<uint4*>(smB);
+      for (int i = tid; i < (int)(3 * kBBytes / 16); i += kTcThreads) dst[i] = __ldg(src + i);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+      // (A part, B part): hi*hi, hi*mid, mid*hi, hi*lo, mid*mid, lo*hi
+      const int pa[6] = {0, 0, 1, 0, 1, 2};
+      const int pb[6] = {0, 1, 0, 2, 1, 0};
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+#pragma unroll
+        for (int j = 0; j < kTcKSteps; ++j) {
+          const uint64_t da = umma_smem_desc(smA_addr + pa[c] * kABytes + 2 * j * kLboA, kLboA, 128);
+          const uint64_t db = umma_smem_desc(smB_addr + pb[c] * kBBytes + 2 * j * kLboB, kLboB, 128);
+          umma_bf16(tmem_base, da, db, kIdesc, (ch | c | j) != 0 ? 1u : 0u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+  }
+  // ---- wait for the last chunk's MMAs
+  {
+    const uint32_t parity = (uint32_t)((p.n_chunks - 1) & 1);
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, q;\n\t}\n"
+          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  __syncthreads();                                    // every thread is past its wait: operands may be overwritten
+
+  // ---- epilogue: TMEM lane = output row (warp w may touch lanes 32 (w % 4) .. + 31), 16 columns per load;
+  //      warps 0-3 take the first half of the column chunks, warps 4-7 the second
+  {
+    const int lane_base = (warp & 3) * 32;
+    const int r = lane_base + lane;
+    constexpr int kChunks = N_TILE / 16;
+    const int c_begin = (warp < 4) ? 0 : (kChunks + 1) / 2;
+    const int c_end = (warp < 4) ? (kChunks + 1) / 2 : kChunks;
+    const bool pow15 = p.mp.power == 1.5f;
+#pragma unroll 1
+    for (int cc = c_begin; cc < c_end; ++cc) {
+      const int c0 = cc * 16;
+      uint32_t v[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = __uint_as_float(v[i]);
+        if (p.mode == 0) {
+          x = fmaxf(1e-10f, x);
+          if (p.out_kind == 1) x = pow15 ? x * sqrtf(x) : exp2f(p.mp.power * log2f(x));
+        } else if (p.out_kind == 2) {
+          x = fmaf(p.mp.n_a, log2f(fmaxf(p.mp.min_amp, x)), p.mp.n_b);
+          x = fminf(fmaxf(x, p.mp.n_lo), p.mp.n_hi);
+        }
+        stage[r * kStageLd + c0 + i] = x;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  // ---- coalesced row-major stores
+  {
+    const int col0 = n_tile * N_TILE;
+    for (int r = warp; r < kTcRows; r += kTcThreads / 32) {
+      const long long row = row0 + r;
+      if (row >= p.mp.rows) break;
+      float* dst = p.out + row * p.ldo + col0;
+      for (int c = lane; c < N_TILE; c += 32)
+        if (col0 + c < p.n_valid) dst[c] = stage[r * kStageLd + c];
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace ttsa

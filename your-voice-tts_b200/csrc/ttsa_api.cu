@@ -14,6 +14,7 @@
 #include "frame_launch.cuh"
 #include "gl_chain.cuh"
 #include "host_tables.hpp"
+#include "mel_gemm_tc.cuh"
 
 using namespace ttsa;
 
@@ -70,6 +71,10 @@ struct ttsa_plan {
   void* d_block = nullptr;         // one allocation holding every table
   const float* d_pinvT = nullptr;  // [num_mels][ldp]
   int ldp = 0;
+  // tensor-core operands: B matrices pre-split into 3 bf16 terms in the canonical UMMA layout (mel_gemm_tc.cuh)
+  const __nv_bfloat16* d_pinv_tc = nullptr;   // pinv: [5 n-tiles of 208 bins][chunks][3][208 x 80]
+  const __nv_bfloat16* d_mel_tc = nullptr;    // mel basis (num_mels == 80 only): [1][13 chunks][3][80 x 80]
+  int pinv_chunks = 0;
 };
 
 struct ttsa_batch {
@@ -165,6 +170,44 @@ static int build_geo(const ttsa_config& c, Geo& g) {
   g.n_a = (float)n_a; g.n_b = (float)n_b; g.n_lo = (float)n_lo; g.n_hi = (float)n_hi;
   g.min_amp = (float)std::pow(10.0, mdb / 20.0);
   return 0;
+}
+
+// fp32 -> bf16 round-to-nearest-even (finite inputs), as __float2bfloat16_rn
+static uint16_t f2bf(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+static float bf2f(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+// B[n_rows x k_cols] (row-major double) -> [n_tile][chunk][part 3][canonical K-major no-swizzle n_tile x 80] bf16
+static std::vector<uint16_t> canon_split_b(const std::vector<double>& B, int n_rows, int k_cols, int n_tile_rows,
+                                           int n_tiles, int n_chunks) {
+  const size_t part = (size_t)n_tile_rows * kTcChunk;
+  std::vector<uint16_t> out((size_t)n_tiles * n_chunks * 3 * part, 0);
+  const size_t lbo = (size_t)(n_tile_rows / 8) * 64;     // in bf16 elements (128 bytes per core matrix)
+  for (int nt = 0; nt < n_tiles; ++nt)
+    for (int ch = 0; ch < n_chunks; ++ch)
+      for (int n = 0; n < n_tile_rows; ++n)
+        for (int kk = 0; kk < kTcChunk; ++kk) {
+          const int row = nt * n_tile_rows + n, k = ch * kTcChunk + kk;
+          const float x = (row < n_rows && k < k_cols) ? (float)B[(size_t)row * k_cols + k] : 0.0f;
+          const uint16_t h = f2bf(x);
+          const float r1 = x - bf2f(h);
+          const uint16_t m = f2bf(r1);
+          const uint16_t l = f2bf(r1 - bf2f(m));
+          const size_t off = (size_t)(kk >> 3) * lbo + (size_t)(n >> 3) * 64 + (size_t)(n & 7) * 8 + (size_t)(kk & 7);
+          const size_t base = ((size_t)nt * n_chunks + ch) * 3 * part;
+          out[base + off] = h;
+          out[base + part + off] = m;
+          out[base + 2 * part + off] = l;
+        }
+  return out;
 }
 
 extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** out) {
@@ -280,13 +323,18 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   for (int k = 0; k < kF; ++k)
     for (int m = 0; m < c.num_mels; ++m) h_pinvT[(size_t)m * p->ldp + k] = (float)p->h_inv_mel[(size_t)k * c.num_mels + m];
 
+  p->pinv_chunks = (c.num_mels + kTcChunk - 1) / kTcChunk;
+  const std::vector<uint16_t> h_pinv_tc = canon_split_b(p->h_inv_mel, kF, c.num_mels, 208, 5, p->pinv_chunks);
+  std::vector<uint16_t> h_mel_tc;
+  if (c.num_mels == 80) h_mel_tc = canon_split_b(p->h_mel, 80, kF, 80, 1, 13);
   // one device block
   struct Piece { const void* src; size_t bytes; size_t off; };
   std::vector<Piece> pieces = {
       {h_tw.data(), h_tw.size() * 4, 0}, {h_g.data(), h_g.size() * 4, 0}, {h_wE.data(), h_wE.size() * 4, 0},
       {h_wO.data(), h_wO.size() * 4, 0}, {h_pw.data(), h_pw.size() * 4, 0}, {h_lo.data(), h_lo.size() * 4, 0},
       {h_cnt.data(), h_cnt.size() * 4, 0}, {h_val.data(), h_val.size() * 4, 0}, {h_pinvT.data(), h_pinvT.size() * 4, 0},
-      {h_wE2.data(), h_wE2.size() * 4, 0}, {h_wO2.data(), h_wO2.size() * 4, 0}};
+      {h_wE2.data(), h_wE2.size() * 4, 0}, {h_wO2.data(), h_wO2.size() * 4, 0},
+      {h_pinv_tc.data(), h_pinv_tc.size() * 2, 0}, {h_mel_tc.data(), h_mel_tc.size() * 2, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -302,6 +350,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->tb.g4 = (const float4*)(base + pieces[1].off);
   p->tb.wE2 = (const float2*)(base + pieces[9].off);
   p->tb.wO2 = (const float2*)(base + pieces[10].off);
+  p->d_pinv_tc = (const __nv_bfloat16*)(base + pieces[11].off);
+  p->d_mel_tc = h_mel_tc.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[12].off);
   p->tb.wE = (const float*)(base + pieces[2].off);
   p->tb.wO = (const float*)(base + pieces[3].off);
   p->tb.pw = (const float*)(base + pieces[4].off);
@@ -339,6 +389,10 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   cudaError_t e = cudaFuncSetAttribute(mel_to_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMtlMaxK * (kMtlBins + kMtlRows) * 4);
   if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "mel kernel configuration: %s", cudaGetErrorString(e)); }
+  e = cudaFuncSetAttribute(gemm_bf16x3_tc_kernel<208>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kTcRows * kTcChunk * 2 + 3 * 208 * kTcChunk * 2);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_bf16x3_tc_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kTcRows * kTcChunk * 2 + 3 * 80 * kTcChunk * 2);
+  if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "tensor-core GEMM configuration: %s", cudaGetErrorString(e)); }
   *out = p;
   return TTSA_OK;
 }
@@ -625,9 +679,20 @@ extern "C" int ttsa_mel_to_linear(const ttsa_plan* plan, const ttsa_batch* batch
   DeviceGuard guard(plan->device);
   MelParams mp = plan->mel;
   mp.rows = batch->total_frames;
-  dim3 grid((kF + kMtlBins - 1) / kMtlBins, (unsigned)((batch->total_frames + kMtlRows - 1) / kMtlRows));
-  const size_t smem = (size_t)mp.num_mels * (kMtlBins + kMtlRows) * 4;
-  mel_to_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mp, plan->d_pinvT, plan->ldp, mel_dev, lin_out_dev, in_kind, out_kind);
+  const char* simt = std::getenv("TTSA_MEL_GEMM");
+  if (simt != nullptr && std::strcmp(simt, "simt") == 0) {      // fp32 SIMT reference kernel (profiling / cross-check)
+    dim3 grid((kF + kMtlBins - 1) / kMtlBins, (unsigned)((batch->total_frames + kMtlRows - 1) / kMtlRows));
+    const size_t smem = (size_t)mp.num_mels * (kMtlBins + kMtlRows) * 4;
+    mel_to_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mp, plan->d_pinvT, plan->ldp, mel_dev, lin_out_dev, in_kind, out_kind);
+  } else {
+    TcGemmParams tp;
+    tp.mp = mp; tp.a = mel_dev; tp.lda = mp.num_mels; tp.k_total = mp.num_mels; tp.n_chunks = plan->pinv_chunks;
+    tp.b = plan->d_pinv_tc; tp.out = lin_out_dev; tp.ldo = kF; tp.n_valid = kF; tp.in_kind = in_kind; tp.out_kind = out_kind;
+    tp.mode = 0;
+    dim3 grid((unsigned)((batch->total_frames + kTcRows - 1) / kTcRows), 5);
+    const size_t smem = 3 * kTcRows * kTcChunk * 2 + 3 * 208 * kTcChunk * 2;
+    gemm_bf16x3_tc_kernel<208><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tp);
+  }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return TTSA_OK;
@@ -642,8 +707,19 @@ extern "C" int ttsa_linear_to_mel(const ttsa_plan* plan, const ttsa_batch* batch
   DeviceGuard guard(plan->device);
   MelParams mp = plan->mel;
   mp.rows = batch->total_frames;
-  const unsigned grid = (unsigned)((batch->total_frames + 7) / 8);
-  linear_to_mel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp, plan->tb, lin_dev, mel_out_dev, in_kind, out_kind);
+  const char* simt = std::getenv("TTSA_MEL_GEMM");
+  if (plan->d_mel_tc == nullptr || (simt != nullptr && std::strcmp(simt, "simt") == 0)) {   // banded fp32 SIMT kernel
+    const unsigned grid = (unsigned)((batch->total_frames + 7) / 8);
+    linear_to_mel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp, plan->tb, lin_dev, mel_out_dev, in_kind, out_kind);
+  } else {
+    TcGemmParams tp;
+    tp.mp = mp; tp.a = lin_dev; tp.lda = kF; tp.k_total = kF; tp.n_chunks = 13;
+    tp.b = plan->d_mel_tc; tp.out = mel_out_dev; tp.ldo = mp.num_mels; tp.n_valid = mp.num_mels; tp.in_kind = in_kind;
+    tp.out_kind = out_kind; tp.mode = 1;
+    dim3 grid((unsigned)((batch->total_frames + kTcRows - 1) / kTcRows), 1);
+    const size_t smem = 3 * kTcRows * kTcChunk * 2 + 3 * 80 * kTcChunk * 2;
+    gemm_bf16x3_tc_kernel<80><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tp);
+  }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return TTSA_OK;
