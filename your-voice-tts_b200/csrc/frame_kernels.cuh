@@ -45,6 +45,7 @@ struct FrameArgs {
   float* sc_acc;          // [B, 2]          GL_ITER with SC: (sum (|X|-S)^2, sum S^2)
   unsigned long long seed;
   int preemph;            // ANALYSIS: apply y[n] - p*y[n-1] while staging
+  int debug;              // profiling only (TTSA_DEBUG): 1 = skip the frame phase, 2 = skip overlap-add + staging work
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -175,6 +176,11 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     for (int i = tid; i < g.win; i += kThreads) wsyn[i] = (i & 1) ? -tb.wO[i >> 1] : tb.wE[i >> 1];
   }
 
+  // programmatic dependent launch: let the next kernel on the stream begin its prologue, and wait here until the
+  // previous kernel's global writes (the waveform this kernel reads, the buffer it overwrites) are complete
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   // contiguous tile range of this CTA over the flattened (utterance, tile) list
   const long long tile_lo = (long long)blockIdx.x * bd.total_tiles / gridDim.x;
   const long long tile_hi = (long long)(blockIdx.x + 1) * bd.total_tiles / gridDim.x;
@@ -267,8 +273,15 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
       const int i0 = t0 * g.hop - g.off0;        // sample index of span position 0
       const bool write_out = jt >= ja;
 
+      if constexpr (MODE != MODE_SYNTH) {
+        // pull the next tile's span towards L2 while this tile is being transformed
+        if (jt + 1 < jb) {
+          const int pi = (jt + 1) * kNF * g.hop - g.off0 + tid * 32;
+          if (pi >= 0 && pi < L && tid * 32 < g.span_len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + pi));
+        }
+      }
       const int t = t0 + warp;
-      if (t < T && t >= first_needed) {
+      if (t < T && t >= first_needed && !(a.debug & 1)) {
         const long long row = frow0 + t;
         const bool own = t >= ja * kNF;            // warm-up frames are copies of another segment's frames
         // 32 complex values per thread as packed pairs: R[m] = (re[2m], re[2m+1]), I[m] = (im[2m], im[2m+1])
@@ -550,11 +563,13 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         }
       }
 
-      __syncthreads();                             // slots complete; planes consumed
+      // next span: its loads are issued by each warp as soon as its frame is done, so they are in flight while the
+      // warp waits for the others and while the tile is overlap-added (the planes are rewritten after that)
       const bool have_next = jt + 1 < jb;
       if constexpr (MODE != MODE_SYNTH) {
-        if (have_next) stage_load(jt + 1);         // next span: loads in flight while this tile is overlap-added
+        if (have_next && !(a.debug & 2)) stage_load(jt + 1);
       }
+      __syncthreads();                             // slots complete; planes consumed
 
       if constexpr (MODE != MODE_ANALYSIS) {
         // -------------------------------------------------------------------- overlap-add + window + 1/(N wss) + store
@@ -569,7 +584,29 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         float* __restrict__ dst = a.wav_out + woff;
         const bool interior = write_out && fv_lo == 0 && fv_hi == kNF && i0 >= 0 && t0 + kNF < T &&
                               i0 + kNF * g.hop <= L && t0 >= ND - 1;
-        for (int rr = tid; rr < g.hop; rr += kThreads) {
+        // finished sample `val` at span position sidx = j*hop + rr: scale and store, or keep as carry
+        auto emit = [&](int j, int rr, int sidx, float val) {
+          if (sidx >= g.span_len) return;
+          if (sidx < out_len) {
+            const int i = i0 + sidx;
+            if (write_out && i >= 0 && i < L) {
+              float inv = pw[rr];
+              if (t0 + j - (g.win - 1 - rr) / g.hop < 0 || t0 + j > T - 1) {   // some overlapping frame does not exist
+                float ws = 0.0f;
+                for (int d = 0, m = rr; m < g.win; ++d, m += g.hop) {
+                  const int tt = t0 + j - d;
+                  if (tt >= 0 && tt < T) ws = fmaf(wsyn[m], wsyn[m], ws);
+                }
+                inv = ws > 1.17549435e-38f ? kInvN / ws : kInvN;              // librosa: divide only where wss > tiny
+              }
+              dst[i] = val * inv;
+            }
+          } else {
+            carry[sidx - out_len] = val;
+          }
+        };
+        if (tid < g.hop && !(a.debug & 2)) {
+          const int rr = tid;
           float acc[kNF + ND - 1];
           float wreg[ND];
           int off[ND];
@@ -602,42 +639,40 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               if (c < g.carry_len) carry[c] = acc[j];
             }
           } else {
-            const int dmax = (g.win - 1 - rr) / g.hop;
 #pragma unroll 1
             for (int j = 0; j < kNF + ND - 1; ++j) {
-              const int sidx = j * g.hop + rr;
               float val = 0.0f;
 #pragma unroll
               for (int jj = 0; jj < kNF + ND - 1; ++jj) val = (jj == j) ? acc[jj] : val;
-              if (sidx >= g.span_len) continue;
-              if (sidx < out_len) {
-                const int i = i0 + sidx;
-                if (write_out && i >= 0 && i < L) {
-                  float inv = pw[rr];
-                  if (t0 + j - dmax < 0 || t0 + j > T - 1) {          // some overlapping frame does not exist
-                    float ws = 0.0f;
-                    for (int d = 0, m = rr; m < g.win; ++d, m += g.hop) {
-                      const int tt = t0 + j - d;
-                      if (tt >= 0 && tt < T) {
-                        const float wv = (m & 1) ? __ldg(tb.wO + (m >> 1)) : __ldg(tb.wE + (m >> 1));
-                        ws = fmaf(wv, wv, ws);
-                      }
-                    }
-                    inv = ws > 1.17549435e-38f ? kInvN / ws : kInvN;   // librosa: divide only where wss > tiny
-                  }
-                  dst[i] = val * inv;
-                }
-              } else {
-                carry[sidx - out_len] = val;
-              }
+              emit(j, rr, j * g.hop + rr, val);
             }
+          }
+        }
+        // residues beyond the thread count (hop 275 = 256 + 19): one small item per (residue, j mod kNF) spread over
+        // all warps, instead of a second full round that only a few lanes of one warp would execute
+        if (g.hop > kThreads && !(a.debug & 2)) {
+          const int nl = g.hop - kThreads;
+          for (int it = tid; it < nl * kNF; it += kThreads) {
+            const int jl = it / nl, rr = kThreads + it - jl * nl;
+            const int sa = jl * g.hop + rr, sb = sa + kNF * g.hop;
+            float va = (has_carry && sa < g.carry_len) ? carry[sa] : 0.0f;
+            float vb = 0.0f;
+            for (int d = 0, m = rr; d < ND && m < g.win; ++d, m += g.hop) {
+              const int po = ((m & 1) ? kSlotPlane : 0) + (m >> 1);
+              const float w = wsyn[m];
+              const int fa = jl - d, fb = fa + kNF;
+              if (fa >= fv_lo && fa < fv_hi) va = fmaf(smem[fa * kBufFloats + po], w, va);
+              if (fb >= fv_lo && fb < fv_hi) vb = fmaf(smem[fb * kBufFloats + po], w, vb);
+            }
+            emit(jl, rr, sa, va);
+            if (jl < ND - 1) emit(jl + kNF, rr, sb, vb);
           }
         }
         has_carry = true;
       }
 
       if constexpr (MODE != MODE_SYNTH) {
-        if (have_next) stage_store(jt + 1);
+        if (have_next && !(a.debug & 2)) stage_store(jt + 1);
       }
       __syncthreads();                             // planes of the next tile ready; slots and carry settled
     }  // tiles of the segment

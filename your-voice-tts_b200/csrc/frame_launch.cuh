@@ -33,11 +33,24 @@ inline const char* set_smem(K kernel, size_t smem_bytes) {
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+// Frame kernels are launched with programmatic dependent launch: the next kernel on the stream may start its
+// prologue (table loads into shared memory) while this one drains; every kernel executes griddepcontrol.wait before it
+// touches global data produced by its predecessor.
 #define TTSA_LAUNCH(KERNEL)                                                        \
   do {                                                                             \
-    KERNEL<<<grid, kThreads, smem, st>>>(g, tb, bd, a);                            \
+    cudaLaunchConfig_t cfg_ = {};                                                  \
+    cfg_.gridDim = dim3((unsigned)grid);                                           \
+    cfg_.blockDim = dim3(kThreads);                                                \
+    cfg_.dynamicSmemBytes = smem;                                                  \
+    cfg_.stream = st;                                                              \
+    cudaLaunchAttribute attr_[1];                                                  \
+    attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;              \
+    attr_[0].val.programmaticStreamSerializationAllowed = 1;                       \
+    cfg_.attrs = attr_;                                                            \
+    cfg_.numAttrs = 1;                                                             \
+    cudaError_t e_ = cudaLaunchKernelEx(&cfg_, KERNEL, g, tb, bd, a);              \
     g_launches += 1;                                                               \
-    cudaError_t e_ = cudaGetLastError();                                           \
+    if (e_ == cudaSuccess) e_ = cudaGetLastError();                                \
     return e_ == cudaSuccess ? nullptr : cudaGetErrorString(e_);                   \
   } while (0)
 

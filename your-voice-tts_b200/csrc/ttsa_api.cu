@@ -653,6 +653,7 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
     b.spec = spec_dev; b.spec_end = spec_dev + (size_t)batch->total_frames * kF;
     b.wav_in = bufs[(i - 1) & 1]; b.wav_out = bufs[i & 1];
     b.wav_end = b.wav_in + batch->total_samples;
+    { const char* dbg = std::getenv("TTSA_DEBUG"); b.debug = dbg ? std::atoi(dbg) : 0; }
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
     if (plan->use_chain) {
       const long long want = (batch->total_frames + kNF - 1) / kNF;
