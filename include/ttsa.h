@@ -98,6 +98,14 @@ int ttsa_batch_from_frames(const ttsa_plan* plan, const int32_t* n_frames_host, 
 /* From per-utterance waveform lengths L[u] (wav inputs; T[u] = 1 + L[u] / hop as librosa.stft with
  * center=True yields -- utils/audio.py:191-197). */
 int ttsa_batch_from_wav_lengths(const ttsa_plan* plan, const int32_t* wav_len_host, int32_t n_utts, ttsa_batch** out);
+/* Strided variants: utterance u's frames live at rows [u*frame_stride, u*frame_stride + T[u]) of the spectrogram
+ * tensors, i.e. the tensors are padded [n_utts, frame_stride, D] blocks as the acoustic models emit them
+ * (models/tacotron2.py:62-73) and as collate_fn builds them (datasets/TTSDataset.py:209-217, utils/data.py:25-31).
+ * Rows beyond T[u] are never read or written.  frame_stride >= max T[u]. */
+int ttsa_batch_from_frames_strided(const ttsa_plan* plan, const int32_t* n_frames_host, int32_t n_utts,
+                                   int64_t frame_stride, ttsa_batch** out);
+int ttsa_batch_from_wav_lengths_strided(const ttsa_plan* plan, const int32_t* wav_len_host, int32_t n_utts,
+                                        int64_t frame_stride, ttsa_batch** out);
 int ttsa_batch_destroy(ttsa_batch* batch);
 int64_t ttsa_batch_total_frames(const ttsa_batch* batch);   /* sum_T: rows of the packed spectrogram tensors */
 int64_t ttsa_batch_total_samples(const ttsa_batch* batch);  /* floats in the packed waveform buffer          */

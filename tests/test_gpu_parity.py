@@ -286,3 +286,49 @@ def test_tensor_in_tensor_out():
     assert isinstance(S, torch.Tensor) and S.is_cuda and S.shape == (1025, 21)
     w = ap.inv_spectrogram(S)
     assert isinstance(w, torch.Tensor) and w.shape == (275 * 20,)
+
+
+# ------------------------------------------------------------------------------------------------ callers either side
+def _ref_prepare_tensor(inputs, out_steps):
+    """utils/data.py:25-31 restated (pad [D, T] arrays to the longest + a zero frame, multiple of out_steps)."""
+    max_len = max(x.shape[1] for x in inputs) + 1
+    rem = max_len % out_steps
+    pad_len = max_len + (out_steps - rem) if rem > 0 else max_len
+    return np.stack([np.pad(x, [[0, 0], [0, pad_len - x.shape[1]]]) for x in inputs])
+
+
+@pytest.mark.parametrize("r", [1, 5])
+def test_collate_features_matches_reference_collate(golden, r):
+    """GPU-side feature half of MyDataset.collate_fn (datasets/TTSDataset.py:191-217) vs the oracle per utterance plus
+    the reference's padding rules."""
+    ap, orc = _ap(TEST_AUDIO), OracleAudioProcessor(**TEST_AUDIO)
+    wav = _wav(golden).astype(np.float32)
+    wavs = [wav[:41885], wav[3000:3000 + 275 * 31 + 7], wav[10000:10000 + 5001]]
+    linear, mel, mel_lengths, stop = ap.collate_features(wavs, outputs_per_step=r)
+    mel_o = [orc.melspectrogram(w) for w in wavs]
+    lin_o = [orc.spectrogram(w) for w in wavs]
+    mel_ref = _ref_prepare_tensor(mel_o, r).transpose(0, 2, 1)
+    lin_ref = _ref_prepare_tensor(lin_o, r).transpose(0, 2, 1)
+    assert tuple(mel.shape) == mel_ref.shape and tuple(linear.shape) == lin_ref.shape and mel.shape[1] % r == 0
+    assert mel_lengths.tolist() == [m.shape[1] + 1 for m in mel_o]
+    m, l = mel.cpu().numpy(), linear.cpu().numpy()
+    assert np.mean(np.abs(m - mel_ref) <= FWD_TOL * ap.max_norm) >= 0.995 and np.abs(m - mel_ref).max() < 5e-3 * ap.max_norm
+    assert np.mean(np.abs(l - lin_ref) <= FWD_TOL * ap.max_norm) >= 0.995 and np.abs(l - lin_ref).max() < 5e-3 * ap.max_norm
+    for u, mo in enumerate(mel_o):                                     # zero frame and padding are exact zeros
+        assert not m[u, mo.shape[1]:].any() and not l[u, mo.shape[1]:].any()
+        assert stop[u, :mo.shape[1]].sum() == 0 and bool((stop[u, mo.shape[1]:] == 1).all())
+
+
+def test_inv_mel_on_padded_model_output():
+    """Griffin-Lim straight from a padded [B, T_max, 80] device tensor (the layout models/tacotron2.py:62-73 returns)."""
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=4)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    Ts, t_max = [23, 9, 40], 48
+    rng = np.random.default_rng(4)
+    mel = rng.random((3, t_max, 80)).astype(np.float32)
+    ang = (2 * np.pi * rng.random((3 * t_max, 1025))).astype(np.float32)
+    wavs = ap.inv_mel_spectrogram_padded(torch.from_numpy(mel).cuda(), Ts, init_angles=torch.from_numpy(ang).cuda())
+    for u, T in enumerate(Ts):
+        yo = orc.inv_mel_spectrogram(mel[u, :T].T, init_angles=ang[u * t_max:u * t_max + T].T)
+        assert wavs[u].shape == (275 * (T - 1),)
+        assert snr_db(yo, wavs[u].cpu().numpy()) >= GL_SNR_DB

@@ -42,6 +42,8 @@ PROTOTYPES = {
     "ttsa_plan_inv_mel_basis": (c_int, [c_void_p, POINTER(c_double)]),
     "ttsa_batch_from_frames": (c_int, [c_void_p, POINTER(c_int32), c_int32, POINTER(c_void_p)]),
     "ttsa_batch_from_wav_lengths": (c_int, [c_void_p, POINTER(c_int32), c_int32, POINTER(c_void_p)]),
+    "ttsa_batch_from_frames_strided": (c_int, [c_void_p, POINTER(c_int32), c_int32, c_int64, POINTER(c_void_p)]),
+    "ttsa_batch_from_wav_lengths_strided": (c_int, [c_void_p, POINTER(c_int32), c_int32, c_int64, POINTER(c_void_p)]),
     "ttsa_batch_destroy": (c_int, [c_void_p]),
     "ttsa_batch_total_frames": (c_int64, [c_void_p]),
     "ttsa_batch_total_samples": (c_int64, [c_void_p]),

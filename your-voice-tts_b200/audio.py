@@ -55,7 +55,7 @@ class _Plan(object):
 class BatchLayout(object):
     """Packed layout of a batch of utterances (ttsa_batch): frame counts, waveform lengths and offsets."""
 
-    def __init__(self, plan, n_frames=None, wav_lengths=None):
+    def __init__(self, plan, n_frames=None, wav_lengths=None, frame_stride=0):
         assert (n_frames is None) != (wav_lengths is None)
         self.plan = plan
         lib = plan.lib
@@ -63,8 +63,10 @@ class BatchLayout(object):
         arr = np.ascontiguousarray(np.asarray(src, dtype=np.int32).reshape(-1))
         self.n_utts = int(arr.shape[0])
         h = ctypes.c_void_p()
-        fn = lib.ttsa_batch_from_frames if n_frames is not None else lib.ttsa_batch_from_wav_lengths
-        L.check(fn(plan.handle, arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), self.n_utts, ctypes.byref(h)))
+        fn = lib.ttsa_batch_from_frames_strided if n_frames is not None else lib.ttsa_batch_from_wav_lengths_strided
+        L.check(fn(plan.handle, arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), self.n_utts,
+                   ctypes.c_int64(int(frame_stride)), ctypes.byref(h)))
+        self.frame_stride = int(frame_stride)
         self.handle = h
         self.total_frames = int(lib.ttsa_batch_total_frames(h))
         self.total_samples = int(lib.ttsa_batch_total_samples(h))
@@ -75,7 +77,8 @@ class BatchLayout(object):
                                        wo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                                        wl.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
         self.frame_off, self.wav_off, self.wav_len = fo, wo, wl
-        self.n_frames = np.diff(fo).astype(np.int64)
+        self.n_frames = (np.asarray(src, dtype=np.int64).reshape(-1) if n_frames is not None
+                         else 1 + wl.astype(np.int64) // plan.cfg.hop_length)
 
     def __del__(self):
         try:
@@ -89,7 +92,7 @@ class BatchLayout(object):
         return [packed[int(self.wav_off[u]):int(self.wav_off[u]) + int(self.wav_len[u])] for u in range(self.n_utts)]
 
     def split_frames(self, packed):
-        return [packed[int(self.frame_off[u]):int(self.frame_off[u + 1])] for u in range(self.n_utts)]
+        return [packed[int(self.frame_off[u]):int(self.frame_off[u]) + int(self.n_frames[u])] for u in range(self.n_utts)]
 
 
 class AudioProcessor(object):
@@ -184,14 +187,15 @@ class AudioProcessor(object):
             _PLAN_CACHE.move_to_end(key)
         return plan
 
-    def layout(self, n_frames=None, wav_lengths=None):
-        """BatchLayout for utterances given by frame counts (spectrogram inputs) or by waveform lengths."""
+    def layout(self, n_frames=None, wav_lengths=None, frame_stride=0):
+        """BatchLayout for utterances given by frame counts (spectrogram inputs) or by waveform lengths.
+        frame_stride > 0: the spectrogram tensors are padded [B, frame_stride, D] blocks instead of packed rows."""
         plan = self._plan()
         src = n_frames if n_frames is not None else wav_lengths
-        key = (id(plan), n_frames is not None, tuple(int(v) for v in np.asarray(src).reshape(-1)))
+        key = (id(plan), n_frames is not None, int(frame_stride), tuple(int(v) for v in np.asarray(src).reshape(-1)))
         lay = self._batch_cache.get(key)
         if lay is None:
-            lay = BatchLayout(plan, n_frames=n_frames, wav_lengths=wav_lengths)
+            lay = BatchLayout(plan, n_frames=n_frames, wav_lengths=wav_lengths, frame_stride=frame_stride)
             self._batch_cache[key] = lay
             while len(self._batch_cache) > 16:
                 self._batch_cache.popitem(last=False)
@@ -236,15 +240,19 @@ class AudioProcessor(object):
         return t.cpu().numpy()
 
     # ------------------------------------------------------------------------------------------ batched API
-    def features_batch(self, wav_packed, layout, want_linear=True, want_mel=True, preemphasis=None):
+    def features_batch(self, wav_packed, layout, want_linear=True, want_mel=True, preemphasis=None, lin_out=None,
+                       mel_out=None):
         """spectrogram() and melspectrogram() of every utterance in one pass (utils/audio.py:138-152).
 
         wav_packed: CUDA float32 [layout.total_samples]; returns (linear [sum_T, num_freq] | None, mel [sum_T, num_mels] | None).
         """
         torch = _torch()
         plan = layout.plan
-        lin = torch.empty((layout.total_frames, self.num_freq), dtype=torch.float32, device=wav_packed.device) if want_linear else None
-        mel = torch.empty((layout.total_frames, self.num_mels), dtype=torch.float32, device=wav_packed.device) if want_mel else None
+        lin, mel = lin_out, mel_out
+        if lin is None and want_linear:
+            lin = torch.empty((layout.total_frames, self.num_freq), dtype=torch.float32, device=wav_packed.device)
+        if mel is None and want_mel:
+            mel = torch.empty((layout.total_frames, self.num_mels), dtype=torch.float32, device=wav_packed.device)
         pre = (self.preemphasis != 0) if preemphasis is None else bool(preemphasis)
         L.check(plan.lib.ttsa_stft_features(plan.handle, layout.handle, self._ptr(wav_packed), self._ptr(lin),
                                             self._ptr(mel), L.FEAT_PREEMPHASIS if pre else 0, self._stream()))
@@ -317,6 +325,51 @@ class AudioProcessor(object):
         return self.griffin_lim_batch(S, layout, L.SPEC_MAGNITUDE, init_angles, seed,
                                       deemphasis=self.preemphasis != 0, return_sc=return_sc, out=out,
                                       workspace=workspace)
+
+    def collate_features(self, wavs, outputs_per_step=1):
+        """The feature half of MyDataset.collate_fn (datasets/TTSDataset.py:191-217 with utils/data.py:25-45) on the
+        GPU: ONE STFT pass yields mel and linear for the whole batch, written straight into zero-padded
+        [B, T_pad, D] tensors (T_pad = longest + 1 zero frame, rounded up to a multiple of outputs_per_step).
+
+        wavs: list of 1-D arrays / tensors (already ordered by the caller).  Returns
+        (linear [B, T_pad, num_freq], mel [B, T_pad, num_mels], mel_lengths [B] (= frames + 1), stop_targets [B, T_pad])."""
+        torch = _torch()
+        dev = self._dev()
+        lens = [int(len(w)) for w in wavs]
+        T = [1 + n // self.hop_length for n in lens]
+        max_len = max(T) + 1                                          # zero-frame (utils/data.py:26)
+        rem = max_len % outputs_per_step
+        pad_len = max_len + (outputs_per_step - rem) if rem > 0 else max_len
+        lay = self.layout(wav_lengths=lens, frame_stride=pad_len)
+        packed = torch.zeros((max(1, lay.total_samples),), dtype=torch.float32, device=dev)
+        for u, w in enumerate(wavs):
+            src = w if self._is_tensor(w) else torch.from_numpy(np.ascontiguousarray(np.asarray(w, dtype=np.float32)))
+            packed[int(lay.wav_off[u]):int(lay.wav_off[u]) + lens[u]].copy_(src.to(dev, torch.float32), non_blocking=True)
+        B = len(wavs)
+        linear = torch.zeros((B, pad_len, self.num_freq), dtype=torch.float32, device=dev)
+        mel = torch.zeros((B, pad_len, self.num_mels), dtype=torch.float32, device=dev)
+        self.features_batch(packed, lay, lin_out=linear.view(B * pad_len, self.num_freq),
+                            mel_out=mel.view(B * pad_len, self.num_mels))
+        mel_lengths = torch.tensor([t + 1 for t in T], dtype=torch.long)
+        # stop targets: zeros for the real frames, ones from the zero-frame on (utils/data.py:34-45)
+        stop_max = max(T) + 1
+        srem = stop_max % outputs_per_step
+        stop_len = stop_max + (outputs_per_step - srem) if srem > 0 else stop_max
+        stop_targets = torch.ones((B, stop_len), dtype=torch.float32)
+        for u, t in enumerate(T):
+            stop_targets[u, :t] = 0.0
+        return linear, mel, mel_lengths, stop_targets
+
+    def inv_mel_spectrogram_padded(self, mel_btd, n_frames, init_angles=None, seed=0):
+        """inv_mel_spectrogram on a model output that stays on the device: mel_btd [B, T_max, num_mels] (the layout
+        models/tacotron2.py:62-73 returns), n_frames[u] valid frames per utterance.  Returns the list of waveforms."""
+        torch = _torch()
+        mel_btd = self._to_dev(mel_btd)
+        B, t_max, _ = mel_btd.shape
+        lay = self.layout(n_frames=[int(t) for t in n_frames], frame_stride=t_max)
+        out = self.inv_mel_spectrogram_batch(mel_btd.reshape(B * t_max, self.num_mels), lay, init_angles=init_angles,
+                                             seed=seed)
+        return lay.split_wav(out)
 
     # ------------------------------------------------------------------------------------------ reference API
     def save_wav(self, wav, path):

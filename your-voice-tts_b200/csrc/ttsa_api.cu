@@ -85,6 +85,7 @@ struct ttsa_batch {
   std::vector<long long> frame_off, wav_off;
   long long total_frames = 0, total_samples = 0;
   int max_chunks = 0;
+  bool dense = true;               // rows of consecutive utterances are contiguous (no per-utterance padding)
   void* d_block = nullptr;
   BatchDev dev;
   const int* d_chunk_off = nullptr;
@@ -419,14 +420,15 @@ extern "C" int ttsa_plan_inv_mel_basis(const ttsa_plan* plan, double* host_out) 
 // ---------------------------------------------------------------------------------------------------------
 // batch layout
 // ---------------------------------------------------------------------------------------------------------
-static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out) {
+static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, long long frame_stride = 0) {
   const int B = b->B;
   b->device = plan->device;
   b->hop = plan->cfg.hop_length;
   b->frame_off.assign(B + 1, 0); b->wav_off.assign(B + 1, 0); b->tile_off.assign(B + 1, 0); b->chunk_off.assign(B + 1, 0);
   b->max_chunks = 0;
   for (int u = 0; u < B; ++u) {
-    b->frame_off[u + 1] = b->frame_off[u] + b->T[u];
+    if (frame_stride > 0 && b->T[u] > frame_stride) { delete b; return fail(TTSA_ERR_BAD_ARG, "frame_stride %lld < frame count %d of utterance %d", frame_stride, b->T[u], u); }
+    b->frame_off[u + 1] = b->frame_off[u] + (frame_stride > 0 ? frame_stride : (long long)b->T[u]);
     b->wav_off[u + 1] = b->wav_off[u] + (b->wav_len[u] + 3) / 4 * 4;
     const long long tiles = (long long)b->tile_off[u] + (b->T[u] + kNF - 1) / kNF;
     if (tiles > std::numeric_limits<int>::max()) { delete b; return fail(TTSA_ERR_BAD_ARG, "batch too large"); }
@@ -436,6 +438,7 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out) 
     b->max_chunks = std::max(b->max_chunks, ch);
   }
   b->total_frames = b->frame_off[B];
+  b->dense = frame_stride <= 0;
   b->total_samples = b->wav_off[B];
   std::memset(&b->dev, 0, sizeof(b->dev));
   b->dev.B = B;
@@ -471,7 +474,12 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out) 
 }
 
 extern "C" int ttsa_batch_from_frames(const ttsa_plan* plan, const int32_t* n_frames_host, int32_t n_utts, ttsa_batch** out) {
-  if (!plan || !n_frames_host || !out || n_utts <= 0) return fail(TTSA_ERR_BAD_ARG, "bad argument");
+  return ttsa_batch_from_frames_strided(plan, n_frames_host, n_utts, 0, out);
+}
+
+extern "C" int ttsa_batch_from_frames_strided(const ttsa_plan* plan, const int32_t* n_frames_host, int32_t n_utts,
+                                              int64_t frame_stride, ttsa_batch** out) {
+  if (!plan || !n_frames_host || !out || n_utts <= 0 || frame_stride < 0) return fail(TTSA_ERR_BAD_ARG, "bad argument");
   *out = nullptr;
   ttsa_batch* b = new ttsa_batch();
   b->B = n_utts;
@@ -481,11 +489,16 @@ extern "C" int ttsa_batch_from_frames(const ttsa_plan* plan, const int32_t* n_fr
     b->T[u] = n_frames_host[u];
     b->wav_len[u] = n_frames_host[u] > 0 ? plan->cfg.hop_length * (n_frames_host[u] - 1) : 0;
   }
-  return batch_finish(plan, b, out);
+  return batch_finish(plan, b, out, frame_stride);
 }
 
 extern "C" int ttsa_batch_from_wav_lengths(const ttsa_plan* plan, const int32_t* wav_len_host, int32_t n_utts, ttsa_batch** out) {
-  if (!plan || !wav_len_host || !out || n_utts <= 0) return fail(TTSA_ERR_BAD_ARG, "bad argument");
+  return ttsa_batch_from_wav_lengths_strided(plan, wav_len_host, n_utts, 0, out);
+}
+
+extern "C" int ttsa_batch_from_wav_lengths_strided(const ttsa_plan* plan, const int32_t* wav_len_host, int32_t n_utts,
+                                                   int64_t frame_stride, ttsa_batch** out) {
+  if (!plan || !wav_len_host || !out || n_utts <= 0 || frame_stride < 0) return fail(TTSA_ERR_BAD_ARG, "bad argument");
   *out = nullptr;
   ttsa_batch* b = new ttsa_batch();
   b->B = n_utts;
@@ -495,7 +508,7 @@ extern "C" int ttsa_batch_from_wav_lengths(const ttsa_plan* plan, const int32_t*
     b->wav_len[u] = wav_len_host[u];
     b->T[u] = 1 + wav_len_host[u] / plan->cfg.hop_length;
   }
-  return batch_finish(plan, b, out);
+  return batch_finish(plan, b, out, frame_stride);
 }
 
 extern "C" int ttsa_batch_destroy(ttsa_batch* batch) {
@@ -655,7 +668,7 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
     b.wav_end = b.wav_in + batch->total_samples;
     { const char* dbg = std::getenv("TTSA_DEBUG"); b.debug = dbg ? std::atoi(dbg) : 0; }
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
-    if (plan->use_chain) {
+    if (plan->use_chain && batch->dense) {
       const long long want = (batch->total_frames + kNF - 1) / kNF;
       const long long max_ctas = (long long)plan->chain_ctas_per_sm * plan->num_sms;
       const int grid = (int)std::max<long long>(1, std::min(want, max_ctas));
