@@ -332,3 +332,24 @@ def test_inv_mel_on_padded_model_output():
         yo = orc.inv_mel_spectrogram(mel[u, :T].T, init_angles=ang[u * t_max:u * t_max + T].T)
         assert wavs[u].shape == (275 * (T - 1),)
         assert snr_db(yo, wavs[u].cpu().numpy()) >= GL_SNR_DB
+
+
+def test_host_pipeline_matches_direct_calls():
+    """Double-buffered host-to-host path (pinned host mel in, pinned host waveform out) == the direct batched call."""
+    from your_voice_tts_b200 import HostPipeline
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=3)
+    ap = _ap(audio)
+    Ts = [30, 12, 45]
+    lay = ap.layout(n_frames=Ts)
+    rng = np.random.default_rng(8)
+    mels = [torch.from_numpy(rng.random((sum(Ts), 80)).astype(np.float32)).pin_memory() for _ in range(4)]
+    outs = [torch.empty((lay.total_samples,), dtype=torch.float32).pin_memory() for _ in range(4)]
+    pipe = HostPipeline(ap, lay)
+    for i in range(4):
+        pipe.submit(mels[i], outs[i], seed=10 + i)
+    pipe.drain()
+    for i in range(4):
+        ref = ap.inv_mel_spectrogram_batch(mels[i].cuda(), lay, seed=10 + i).cpu()
+        for u in range(len(Ts)):
+            a, b = lay.split_wav(outs[i])[u], lay.split_wav(ref)[u]
+            assert torch.equal(a, b)

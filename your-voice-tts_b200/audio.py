@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib as L
 
-__all__ = ["AudioProcessor", "BatchLayout"]
+__all__ = ["AudioProcessor", "BatchLayout", "HostPipeline"]
 
 _PLAN_CACHE = OrderedDict()
 _PLAN_CACHE_MAX = 32
@@ -93,6 +93,50 @@ class BatchLayout(object):
 
     def split_frames(self, packed):
         return [packed[int(self.frame_off[u]):int(self.frame_off[u]) + int(self.n_frames[u])] for u in range(self.n_utts)]
+
+
+class HostPipeline(object):
+    """Host-to-host batched inv_mel_spectrogram with the copies hidden behind the compute of neighbouring batches.
+
+    submit(mel_host, wav_host, seed) enqueues: pinned-host mel -> device (compute stream), mel -> linear ->
+    Griffin-Lim -> de-emphasis (compute stream), device waveform -> pinned host (copy stream).  Two device buffer sets
+    alternate, so the D2H copy of batch i overlaps the kernels of batch i+1.  `wav_host` is valid after the returned
+    event (or drain())."""
+
+    def __init__(self, ap, layout):
+        torch = _torch()
+        self.ap, self.layout = ap, layout
+        dev = ap._dev()
+        self.comp, self.copy = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        n = max(1, layout.total_samples)
+        self.mel_dev = [torch.empty((layout.total_frames, ap.num_mels), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.wav_dev = [torch.zeros((n,), dtype=torch.float32, device=dev) for _ in range(2)]
+        ws_bytes = int(layout.plan.lib.ttsa_griffin_lim_workspace_bytes(layout.plan.handle, layout.handle))
+        self.ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        self.comp_done = [torch.cuda.Event() for _ in range(2)]
+        self.copy_done = [torch.cuda.Event() for _ in range(2)]
+        self.count = 0
+
+    def submit(self, mel_host, wav_host, seed=0):
+        torch = _torch()
+        b = self.count & 1
+        with torch.cuda.stream(self.comp):
+            if self.count >= 2:
+                self.comp.wait_event(self.copy_done[b])        # the buffers of batch i-2 have been drained
+            self.mel_dev[b].copy_(mel_host, non_blocking=True)
+            self.ap.inv_mel_spectrogram_batch(self.mel_dev[b], self.layout, seed=seed, out=self.wav_dev[b],
+                                              workspace=self.ws)
+            self.comp_done[b].record(self.comp)
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(self.comp_done[b])
+            wav_host.copy_(self.wav_dev[b], non_blocking=True)
+            self.copy_done[b].record(self.copy)
+        self.count += 1
+        return self.copy_done[b]
+
+    def drain(self):
+        self.comp.synchronize()
+        self.copy.synchronize()
 
 
 class AudioProcessor(object):
