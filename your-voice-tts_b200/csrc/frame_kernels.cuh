@@ -51,7 +51,7 @@ struct FrameArgs {
 // ---------------------------------------------------------------------------------------------------------
 // counter-based RNG (Philox4x32-10) for the initial phases when none are injected
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigned long long ctr) {
+__device__ __forceinline__ float4 philox_uniform4(unsigned long long seed, unsigned long long ctr) {
   unsigned int c0 = (unsigned int)ctr, c1 = (unsigned int)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
   unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
 #pragma unroll
@@ -62,7 +62,8 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigne
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  return (float)(c0 >> 8) * (1.0f / 16777216.0f);   // [0, 1)
+  constexpr float s = 1.0f / 16777216.0f;   // [0, 1)
+  return make_float4((float)(c0 >> 8) * s, (float)(c1 >> 8) * s, (float)(c2 >> 8) * s, (float)(c3 >> 8) * s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -372,21 +373,32 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               } else {
                 // SYNTH: Y given directly (complex input, or magnitude with injected / generated phases), expressed in
                 // the shifted frame:  Y'[k] = Y[k] exp(+j 2 pi k lpad / n_fft)
+                // Generated phases (no injected angles): one Philox4x32-10 call per (frame, m, lane) yields the four
+                // uniforms of this step's four bins.  A uniformly random phase stays uniformly random under the
+                // deterministic shift ramp, so generated phases are defined directly in the shifted frame.
                 float2 y[4];
+                float u4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                const bool gen = SRC != SRC_COMPLEX && a.angles == nullptr;
+                if (gen) {
+                  const float4 q = philox_uniform4(a.seed, ((unsigned long long)row * 16ull + (unsigned long long)m) * 32ull + (unsigned long long)lane);
+                  u4[0] = q.x; u4[1] = q.y; u4[2] = q.z; u4[3] = q.w;
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const int k = (e & 1) ? 1024 - (k0 + 32 * (e >> 1)) : k0 + 32 * (e >> 1);   // k0, 1024-k0, k0+32, 992-k0
-                  float2 val;
                   if constexpr (SRC == SRC_COMPLEX) {
-                    val = (reinterpret_cast<const float2*>(a.cplx_in) + row * kF)[k];
+                    y[e] = cmul((reinterpret_cast<const float2*>(a.cplx_in) + row * kF)[k], shift_phasor(k, lpad, 1.0f));
                   } else {
                     const float S = spec_to_mag<SRC>(__ldg(a.spec + row * kF + k), g);
                     float sn, cs;
-                    if (a.angles != nullptr) sincosf(__ldg(a.angles + row * kF + k), &sn, &cs);
-                    else sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + k)), &sn, &cs);
-                    val = make_float2(S * cs, S * sn);
+                    if (gen) {
+                      __sincosf(6.2831853071795864769f * u4[e], &sn, &cs);
+                      y[e] = make_float2(S * cs, S * sn);
+                    } else {
+                      sincosf(__ldg(a.angles + row * kF + k), &sn, &cs);
+                      y[e] = cmul(make_float2(S * cs, S * sn), shift_phasor(k, lpad, 1.0f));
+                    }
                   }
-                  y[e] = cmul(val, shift_phasor(k, lpad, 1.0f));
                 }
                 if (m == 0 && l0) { y[0].y = 0.0f; y[1].y = 0.0f; }     // irfft ignores Im of DC / Nyquist
                 YkR = make_float2(y[0].x, y[2].x); YkI = make_float2(y[0].y, y[2].y);
@@ -422,9 +434,13 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               } else {
                 const float S5 = spec_to_mag<SRC>(__ldg(a.spec + row * kF + 512), g);
                 float s5, c5;
-                if (a.angles != nullptr) sincosf(__ldg(a.angles + row * kF + 512), &s5, &c5);
-                else sincospif(2.0f * philox_uniform(a.seed, (unsigned long long)(row * kF + 512)), &s5, &c5);
-                Y = cmul(make_float2(S5 * c5, S5 * s5), shift_phasor(512, lpad, 1.0f));
+                if (a.angles != nullptr) {
+                  sincosf(__ldg(a.angles + row * kF + 512), &s5, &c5);
+                  Y = cmul(make_float2(S5 * c5, S5 * s5), shift_phasor(512, lpad, 1.0f));
+                } else {
+                  __sincosf(6.2831853071795864769f * philox_uniform4(a.seed, ((unsigned long long)row * 16ull + 8ull) * 32ull).x, &s5, &c5);
+                  Y = make_float2(S5 * c5, S5 * s5);
+                }
               }
               z512 = make_float2(2.0f * Y.x, 2.0f * Y.y);
             }
