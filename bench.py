@@ -133,8 +133,8 @@ class ClockSampler(object):
 def _cpu_worker(args):
     import numpy as np
     from oracle.audio_oracle import OracleAudioProcessor
-    mel_dt, seed = args
-    orc = OracleAudioProcessor(**AUDIO)
+    mel_dt, seed, iters = args
+    orc = OracleAudioProcessor(**dict(AUDIO, griffin_lim_iters=iters))
     np.random.seed(seed)
     y = orc.inv_mel_spectrogram(mel_dt)          # [80, T] -> wav, 60 iterations, exactly the reference's call
     return len(y)
@@ -155,9 +155,9 @@ def cpu_reference_run(n_utts, cores):
         os.environ[var] = "1"                                  # one thread per worker process, no oversubscription
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(mel[:, :8], 0)] * cores)      # process start-up and imports, untimed
+        pool.map(_cpu_worker, [(mel[:, :8], 0, 2)] * cores)   # process start-up and imports, untimed
         t0 = time.perf_counter()
-        lens = pool.map(_cpu_worker, [(mel, 100 + i) for i in range(n_utts)])
+        lens = pool.map(_cpu_worker, [(mel, 100 + i, ITERS) for i in range(n_utts)])
         dt = time.perf_counter() - t0
     return sum(lens) / SR / dt, dt
 
@@ -185,8 +185,8 @@ def run_reference(args, rank):
             vals.append((v, dt))
     value = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
-    sample = "%d utterances (one per host thread) x inv_mel_spectrogram 60 iters per step, %d of %d requested steps" % (
-        per_step, n_steps, args.steps)
+    sample = "%d utterances (one per host thread) x inv_mel_spectrogram %d iters per step, %d of %d requested steps" % (
+        per_step, ITERS, n_steps, args.steps)
     line = {"impl": "reference", "metric": "griffin_lim_audio_sec_per_sec", "value": value, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": n_steps, "warmup": n_warm, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -213,9 +213,12 @@ def main():
     ap_.add_argument("--warmup", type=int, default=3)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap_.add_argument("--batch", type=int, default=64, help="utterances per GPU")
+    ap_.add_argument("--iters", type=int, default=ITERS, help="Griffin-Lim iterations (BASELINE configs[4] sweeps 30 and 60)")
     ap_.add_argument("--no-cpu-baseline", action="store_true")
     ap_.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
     args = ap_.parse_args()
+    globals()["ITERS"] = int(args.iters)
+    AUDIO["griffin_lim_iters"] = int(args.iters)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -385,7 +388,7 @@ def main():
         cores = host_cores()
         v, dt = cpu_reference_run(cores, cores)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                "sample": "%d utterances (one per host thread) x inv_mel_spectrogram 60 iters, %.1f s wall" % (cores, dt)}
+                                "sample": "%d utterances (one per host thread) x inv_mel_spectrogram %d iters, %.1f s wall" % (cores, ITERS, dt)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -129,3 +129,16 @@ def test_host_helpers_match_reference_formulas(golden):
     np.testing.assert_allclose(ap.dequantize(ap.quantize(x, 9), 9), x, atol=1e-12)
     wav = golden["wav_i16"].astype(np.float64) / 32768.0
     assert ap.find_endpoint(wav) == orc.find_endpoint(wav)
+
+
+def test_strided_batch_layout():
+    """Padded [B, frame_stride, D] layouts (model outputs, collate tensors): rows of utterance u start at u*stride."""
+    ap, plan = _host_plan(MAIN_AUDIO)
+    lay = pkg.BatchLayout(plan, n_frames=[23, 9, 40], frame_stride=48)
+    assert list(lay.frame_off) == [0, 48, 96, 144] and lay.total_frames == 144
+    assert list(lay.n_frames) == [23, 9, 40] and list(lay.wav_len) == [275 * 22, 275 * 8, 275 * 39]
+    lay2 = pkg.BatchLayout(plan, wav_lengths=[5000, 2750], frame_stride=20)
+    assert list(lay2.n_frames) == [19, 11] and list(lay2.frame_off) == [0, 20, 40]
+    with pytest.raises(L.TtsaError) as ei:
+        pkg.BatchLayout(plan, n_frames=[23, 50], frame_stride=48)
+    assert ei.value.code == L.TTSA_ERR_BAD_ARG
