@@ -223,3 +223,166 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_tc_kernel(const TcG
 }
 
 }  // namespace ttsa
+
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined mel -> linear (num_mels <= 80): one CTA walks the N tiles of a 128-frame M tile.
+//   A (mel amplitudes, 3 bf16 terms) is converted once and stays in shared memory;
+//   B tiles (pseudo-inverse rows) stream in with cp.async into two alternating buffers;
+//   the accumulator alternates between two TMEM regions, so the MMAs of N tile nt run while tile nt-1 drains:
+//   tcgen05.ld -> clamp/power -> shared-memory staging -> coalesced row stores.
+// ---------------------------------------------------------------------------------------------------------
+namespace ttsa {
+
+constexpr int kM2lN = 96;                         // UMMA N of the pipelined kernel; 11 tiles cover 1056 >= 1025 bins
+constexpr int kM2lTiles = 11;
+constexpr int kM2lThreads = 512;
+constexpr int kM2lStageLd = kM2lN + 1;
+constexpr uint32_t kM2lABytes = kTcRows * kTcChunk * 2;          // 20 480 per part
+constexpr uint32_t kM2lBBytes = kM2lN * kTcChunk * 2;            // 15 360 per part
+constexpr size_t kM2lSmem = 3 * kM2lABytes + 2 * 3 * kM2lBBytes + (size_t)kTcRows * kM2lStageLd * 4;
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}\n"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(kM2lThreads, 1) mel_to_linear_tc_kernel(const TcGemmParams p, const int n_mtiles) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  constexpr uint32_t kLboA = (kTcRows / 8) * 128, kLboB = (kM2lN / 8) * 128;
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kM2lN >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+  unsigned char* const smA = tc_smem;
+  unsigned char* const smB = tc_smem + 3 * kM2lABytes;                       // two buffers of 3 parts
+  float* const stage = reinterpret_cast<float*>(tc_smem + 3 * kM2lABytes + 2 * 3 * kM2lBBytes);
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[1])) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&mbar[0]);
+  const uint32_t smA_addr = (uint32_t)__cvta_generic_to_shared(smA);
+  const uint32_t smB_addr = (uint32_t)__cvta_generic_to_shared(smB);
+  const bool pow15 = p.mp.power == 1.5f;
+  uint32_t uses[2] = {0, 0};                       // completed uses of each accumulator / mbarrier (phase parity)
+
+  auto load_b = [&](int nt) {                      // pseudo-inverse rows of N tile nt -> buffer nt & 1 (async)
+    const uint4* src = reinterpret_cast<const uint4*>(p.b) + (size_t)nt * (3 * kM2lBBytes / 16);
+    unsigned char* dst = smB + (nt & 1) * 3 * kM2lBBytes;
+    for (int i = tid; i < (int)(3 * kM2lBBytes / 16); i += kM2lThreads) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 16 * i);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
+    }
+  };
+  auto epilogue = [&](int nt, long long row0) {    // drain accumulator nt & 1
+    const int b = nt & 1;
+    mbar_wait(bar0 + 8 * b, uses[b] & 1);
+    uses[b] += 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int lane_base = (warp & 3) * 32;
+    const int r = lane_base + lane;
+#pragma unroll 1
+    for (int cc = (warp >> 2); cc < kM2lN / 8; cc += kM2lThreads / 128) {     // 12 chunks of 8 columns over 4 warp groups
+      uint32_t v[8];
+      const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(b * kM2lN + cc * 8);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x = fmaxf(1e-10f, __uint_as_float(v[i]));
+        if (p.out_kind == 1) x = pow15 ? x * sqrtf(x) : exp2f(p.mp.power * log2f(x));
+        stage[r * kM2lStageLd + cc * 8 + i] = x;
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    const int col0 = nt * kM2lN;
+    for (int idx = tid; idx < kTcRows * kM2lN; idx += kM2lThreads) {
+      const int rr = idx / kM2lN, c = idx - rr * kM2lN;
+      const long long row = row0 + rr;
+      if (row < p.mp.rows && col0 + c < p.n_valid) p.out[row * p.ldo + col0 + c] = stage[rr * kM2lStageLd + c];
+    }
+  };
+
+  for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+    const long long row0 = (long long)mt * kTcRows;
+    __syncthreads();                                // previous M tile fully drained (staging, A, B reusable)
+    load_b(0);
+    // ---- A: fp32 mel -> amplitude -> three bf16 terms; thread (row, half) converts 5 K blocks of 8
+    if (tid < 256) {
+      const int r = tid >> 1, half = tid & 1;
+      const long long row = row0 + r;
+#pragma unroll 1
+      for (int kb = half * 5; kb < half * 5 + 5; ++kb) {
+        __align__(16) __nv_bfloat16 h8[8], m8[8], l8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = kb * 8 + i;
+          float x = 0.0f;
+          if (row < p.mp.rows && k < p.k_total) x = mel_in_value(__ldg(p.a + row * p.lda + k), p.in_kind, p.mp);
+          h8[i] = __float2bfloat16_rn(x);
+          const float r1 = x - __bfloat162float(h8[i]);
+          m8[i] = __float2bfloat16_rn(r1);
+          l8[i] = __float2bfloat16_rn(r1 - __bfloat162float(m8[i]));
+        }
+        const uint32_t off = (uint32_t)kb * kLboA + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+        *reinterpret_cast<uint4*>(smA + off) = *reinterpret_cast<const uint4*>(h8);
+        *reinterpret_cast<uint4*>(smA + kM2lABytes + off) = *reinterpret_cast<const uint4*>(m8);
+        *reinterpret_cast<uint4*>(smA + 2 * kM2lABytes + off) = *reinterpret_cast<const uint4*>(l8);
+      }
+    }
+    for (int nt = 0; nt < kM2lTiles; ++nt) {
+      asm volatile("cp.async.wait_all;" ::: "memory");                 // B(nt) has landed (this thread's part)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tid == 0) {
+        const int pa[6] = {0, 0, 1, 0, 1, 2};
+        const int pb[6] = {0, 1, 0, 2, 1, 0};
+        const uint32_t bbase = smB_addr + (nt & 1) * 3 * kM2lBBytes;
+        const uint32_t dcol = tmem_base + (uint32_t)((nt & 1) * kM2lN);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+#pragma unroll
+          for (int j = 0; j < kTcKSteps; ++j) {
+            const uint64_t da = umma_smem_desc(smA_addr + pa[c] * kM2lABytes + 2 * j * kLboA, kLboA, 128);
+            const uint64_t db = umma_smem_desc(bbase + pb[c] * kM2lBBytes + 2 * j * kLboB, kLboB, 128);
+            umma_bf16(dcol, da, db, kIdesc, (c | j) != 0 ? 1u : 0u);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * (nt & 1)) : "memory");
+      }
+      // the other B buffer was last read by the MMAs of tile nt-1, whose completion epilogue(nt-1) below waits for;
+      // tile nt-2's were waited for one iteration ago, so the buffer of tile nt+1 (= that of nt-1) is free only after
+      // that wait: issue the next copy after the epilogue's wait
+      if (nt >= 1) epilogue(nt - 1, row0);
+      if (nt + 1 < kM2lTiles) load_b(nt + 1);
+    }
+    epilogue(kM2lTiles - 1, row0);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+}  // namespace ttsa

@@ -74,6 +74,7 @@ struct ttsa_plan {
   // tensor-core operands: B matrices pre-split into 3 bf16 terms in the canonical UMMA layout (mel_gemm_tc.cuh)
   const __nv_bfloat16* d_pinv_tc = nullptr;   // pinv: [5 n-tiles of 208 bins][chunks][3][208 x 80]
   const __nv_bfloat16* d_mel_tc = nullptr;    // mel basis (num_mels == 80 only): [1][13 chunks][3][80 x 80]
+  const __nv_bfloat16* d_pinv_tc96 = nullptr; // pinv for the pipelined kernel (num_mels <= 80): [11 n-tiles of 96][3][96 x 80]
   int pinv_chunks = 0;
 };
 
@@ -328,6 +329,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   const std::vector<uint16_t> h_pinv_tc = canon_split_b(p->h_inv_mel, kF, c.num_mels, 208, 5, p->pinv_chunks);
   std::vector<uint16_t> h_mel_tc;
   if (c.num_mels == 80) h_mel_tc = canon_split_b(p->h_mel, 80, kF, 80, 1, 13);
+  std::vector<uint16_t> h_pinv_tc96;
+  if (p->pinv_chunks == 1) h_pinv_tc96 = canon_split_b(p->h_inv_mel, kF, c.num_mels, kM2lN, kM2lTiles, 1);
   // one device block
   struct Piece { const void* src; size_t bytes; size_t off; };
   std::vector<Piece> pieces = {
@@ -335,7 +338,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       {h_wO.data(), h_wO.size() * 4, 0}, {h_pw.data(), h_pw.size() * 4, 0}, {h_lo.data(), h_lo.size() * 4, 0},
       {h_cnt.data(), h_cnt.size() * 4, 0}, {h_val.data(), h_val.size() * 4, 0}, {h_pinvT.data(), h_pinvT.size() * 4, 0},
       {h_wE2.data(), h_wE2.size() * 4, 0}, {h_wO2.data(), h_wO2.size() * 4, 0},
-      {h_pinv_tc.data(), h_pinv_tc.size() * 2, 0}, {h_mel_tc.data(), h_mel_tc.size() * 2, 0}};
+      {h_pinv_tc.data(), h_pinv_tc.size() * 2, 0}, {h_mel_tc.data(), h_mel_tc.size() * 2, 0},
+      {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -353,6 +357,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->tb.wO2 = (const float2*)(base + pieces[10].off);
   p->d_pinv_tc = (const __nv_bfloat16*)(base + pieces[11].off);
   p->d_mel_tc = h_mel_tc.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[12].off);
+  p->d_pinv_tc96 = h_pinv_tc96.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[13].off);
   p->tb.wE = (const float*)(base + pieces[2].off);
   p->tb.wO = (const float*)(base + pieces[3].off);
   p->tb.pw = (const float*)(base + pieces[4].off);
@@ -393,6 +398,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   e = cudaFuncSetAttribute(gemm_bf16x3_tc_kernel<208>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kTcRows * kTcChunk * 2 + 3 * 208 * kTcChunk * 2);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(gemm_bf16x3_tc_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kTcRows * kTcChunk * 2 + 3 * 80 * kTcChunk * 2);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mel_to_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kM2lSmem);
   if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "tensor-core GEMM configuration: %s", cudaGetErrorString(e)); }
   *out = p;
   return TTSA_OK;
@@ -698,6 +704,15 @@ extern "C" int ttsa_mel_to_linear(const ttsa_plan* plan, const ttsa_batch* batch
     dim3 grid((kF + kMtlBins - 1) / kMtlBins, (unsigned)((batch->total_frames + kMtlRows - 1) / kMtlRows));
     const size_t smem = (size_t)mp.num_mels * (kMtlBins + kMtlRows) * 4;
     mel_to_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mp, plan->d_pinvT, plan->ldp, mel_dev, lin_out_dev, in_kind, out_kind);
+  } else if (plan->d_pinv_tc96 != nullptr && !(simt != nullptr && std::strcmp(simt, "tc_simple") == 0)) {
+    // pipelined tensor-core kernel: one CTA per 128-frame tile walks all bin tiles
+    TcGemmParams tp;
+    tp.mp = mp; tp.a = mel_dev; tp.lda = mp.num_mels; tp.k_total = mp.num_mels; tp.n_chunks = 1;
+    tp.b = plan->d_pinv_tc96; tp.out = lin_out_dev; tp.ldo = kF; tp.n_valid = kF; tp.in_kind = in_kind; tp.out_kind = out_kind;
+    tp.mode = 0;
+    const int n_mtiles = (int)((batch->total_frames + kTcRows - 1) / kTcRows);
+    const int grid = n_mtiles < plan->num_sms ? n_mtiles : plan->num_sms;
+    mel_to_linear_tc_kernel<<<grid, kM2lThreads, kM2lSmem, (cudaStream_t)stream>>>(tp, n_mtiles);
   } else {
     TcGemmParams tp;
     tp.mp = mp; tp.a = mel_dev; tp.lda = mp.num_mels; tp.k_total = mp.num_mels; tp.n_chunks = plan->pinv_chunks;
