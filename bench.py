@@ -373,7 +373,8 @@ def main():
     roofline = {"kernel": "frame_kernel<MODE_GL_ITER> (one Griffin-Lim iteration over the batch)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": iter_ms,
-                "share_of_step": ITERS * iter_ms / ms_per_step}
+                "share_of_step": ITERS * iter_ms / ms_per_step,
+                "init_synthesis_ms": t_init}
 
     line = {"metric": "griffin_lim_audio_sec_per_sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

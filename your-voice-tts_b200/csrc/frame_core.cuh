@@ -42,26 +42,6 @@ __device__ __forceinline__ void transform_pass(float2 (&R)[16], float2 (&I)[16],
   }
 }
 
-// Asynchronous copy of `n` consecutive floats starting at `ptr` (4-byte aligned) into dst with 16-byte chunks taken
-// from the enclosing 16-byte-aligned range: element k lands at dst[off + k], off = returned value (0..3).  Chunks that
-// would touch memory outside [lo, hi) fall back to 4-byte copies of the in-range elements.
-__device__ __forceinline__ int span_to_smem_async(float* dst, const float* ptr, int n, const float* lo, const float* hi, int lane) {
-  const int off = (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ull);
-  const float* base = ptr - off;                      // 16-byte aligned
-  const int nchunks = (off + n + 3) >> 2;
-  for (int c = lane; c < nchunks; c += 32) {
-    const float* gsrc = base + 4 * c;
-    if (gsrc >= lo && gsrc + 4 <= hi) {
-      cp_async16(dst + 4 * c, gsrc);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (gsrc + e >= lo && gsrc + e < hi) cp_async4(dst + 4 * c + e, gsrc + e);
-    }
-  }
-  return off;
-}
-
 // Griffin-Lim per-bin step (utils/audio.py:187-188): X -> Y = |S| X/|X| on the real-FFT bins, expressed on the packed
 // 1024-point spectrum.  In: element k1 of lane L = Z[32 k1 + L].  Out: conj(Z') ready for the forward transform that
 // implements the inverse.  Bin k pairs with 1024 - k, held by lane (32 - L) & 31 in register 31 - k1 (lane 0: its own

@@ -34,6 +34,7 @@ enum { OUT_COMPLEX = 0, OUT_FEATURES = 1 };               // ANALYSIS output kin
 struct FrameArgs {
   const float* spec;      // [sum_T, F]      GL_ITER / SYNTH (mag or normalised dB)
   const float* spec_end;  // one past the last element of spec (bounds for the 16-byte row copies)
+  long long rows_total;   // rows of the spectrogram-domain tensors (bounds for angles / complex row copies)
   const float* angles;    // [sum_T, F]      SYNTH: initial phases in radians, or nullptr -> counter RNG
   const float* cplx_in;   // [sum_T, F, 2]   SYNTH with SRC_COMPLEX
   const float* wav_in;    // packed wav      GL_ITER (previous y) / ANALYSIS
@@ -79,14 +80,14 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Asynchronous copy of one spectrogram row (kF floats, 4-byte aligned) into the warp's exchange buffer with 16-byte
-// chunks taken from the enclosing 16-byte-aligned range; element k lands at dst[off + k], off = returned value.
-// Chunks that would touch memory outside [lo, hi) fall back to 4-byte copies of the in-range elements.
-__device__ __forceinline__ int row_to_smem_async(float* dst, const float* row_ptr, const float* lo, const float* hi, int lane) {
-  const int off = (int)((reinterpret_cast<unsigned long long>(row_ptr) >> 2) & 3ull);
-  const float* base = row_ptr - off;                      // 16-byte aligned
-  const int nchunks = (off + kF + 3) >> 2;
-  if (base >= lo && base + 4 * nchunks <= hi) {           // every chunk inside the tensor (all rows but the last)
+// Asynchronous copy of `n` consecutive floats starting at `ptr` (4-byte aligned) into dst with 16-byte chunks taken
+// from the enclosing 16-byte-aligned range: element k lands at dst[off + k], off = returned value (0..3).  Chunks that
+// would touch memory outside [lo, hi) fall back to 4-byte copies of the in-range elements.
+__device__ __forceinline__ int span_to_smem_async(float* dst, const float* ptr, int n, const float* lo, const float* hi, int lane) {
+  const int off = (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ull);
+  const float* base = ptr - off;                      // 16-byte aligned
+  const int nchunks = (off + n + 3) >> 2;
+  if (base >= lo && base + 4 * nchunks <= hi) {       // every chunk inside the tensor (all rows but the first / last)
     for (int c = lane; c < nchunks; c += 32) cp_async16(dst + 4 * c, base + 4 * c);
     return off;
   }
@@ -101,6 +102,10 @@ __device__ __forceinline__ int row_to_smem_async(float* dst, const float* row_pt
     }
   }
   return off;
+}
+// one spectrogram row (kF floats)
+__device__ __forceinline__ int row_to_smem_async(float* dst, const float* row_ptr, const float* lo, const float* hi, int lane) {
+  return span_to_smem_async(dst, row_ptr, kF, lo, hi, lane);
 }
 
 // magnitude of one spectrogram value
@@ -333,7 +338,24 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               cp_async_wait_all();                   // this frame's |S| row (issued between the two forward passes)
               __syncwarp();
             }
+            int a_off = 0;
+            if constexpr (MODE == MODE_SYNTH) {
+              // stage this frame's input rows in the (idle) exchange buffer: one exposed HBM round trip per frame
+              // instead of one per group of bins
+              __syncwarp();
+              if constexpr (SRC == SRC_COMPLEX) {
+                s_off = span_to_smem_async(buf, a.cplx_in + row * (2 * kF), 2 * kF, a.cplx_in,
+                                           a.cplx_in + a.rows_total * (2 * kF), lane);
+              } else {
+                s_off = row_to_smem_async(buf, a.spec + row * kF, a.spec, a.spec_end, lane);
+                if (a.angles != nullptr)
+                  a_off = 1040 + row_to_smem_async(buf + 1040, a.angles + row * kF, a.angles, a.angles + a.rows_total * kF, lane);
+              }
+              cp_async_wait_all();
+              __syncwarp();
+            }
             const float* srow = buf + s_off;
+            const float* arow = buf + a_off;
             float2 SR[8], SI[8];
             float2 z512 = make_float2(0.0f, 0.0f);
             static_for<0, 8>([&](auto mc) {
@@ -387,15 +409,15 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
                 for (int e = 0; e < 4; ++e) {
                   const int k = (e & 1) ? 1024 - (k0 + 32 * (e >> 1)) : k0 + 32 * (e >> 1);   // k0, 1024-k0, k0+32, 992-k0
                   if constexpr (SRC == SRC_COMPLEX) {
-                    y[e] = cmul((reinterpret_cast<const float2*>(a.cplx_in) + row * kF)[k], shift_phasor(k, lpad, 1.0f));
+                    y[e] = cmul(make_float2(srow[2 * k], srow[2 * k + 1]), shift_phasor(k, lpad, 1.0f));
                   } else {
-                    const float S = spec_to_mag<SRC>(__ldg(a.spec + row * kF + k), g);
+                    const float S = spec_to_mag<SRC>(srow[k], g);
                     float sn, cs;
                     if (gen) {
                       __sincosf(6.2831853071795864769f * u4[e], &sn, &cs);
                       y[e] = make_float2(S * cs, S * sn);
                     } else {
-                      sincosf(__ldg(a.angles + row * kF + k), &sn, &cs);
+                      sincosf(arow[k], &sn, &cs);
                       y[e] = cmul(make_float2(S * cs, S * sn), shift_phasor(k, lpad, 1.0f));
                     }
                   }
@@ -430,12 +452,12 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
                   sc_den += S5 * S5;
                 }
               } else if constexpr (SRC == SRC_COMPLEX) {
-                Y = cmul((reinterpret_cast<const float2*>(a.cplx_in) + row * kF)[512], shift_phasor(512, lpad, 1.0f));
+                Y = cmul(make_float2(srow[1024], srow[1025]), shift_phasor(512, lpad, 1.0f));
               } else {
-                const float S5 = spec_to_mag<SRC>(__ldg(a.spec + row * kF + 512), g);
+                const float S5 = spec_to_mag<SRC>(srow[512], g);
                 float s5, c5;
                 if (a.angles != nullptr) {
-                  sincosf(__ldg(a.angles + row * kF + 512), &s5, &c5);
+                  sincosf(arow[512], &s5, &c5);
                   Y = cmul(make_float2(S5 * c5, S5 * s5), shift_phasor(512, lpad, 1.0f));
                 } else {
                   __sincosf(6.2831853071795864769f * philox_uniform4(a.seed, ((unsigned long long)row * 16ull + 8ull) * 32ull).x, &s5, &c5);

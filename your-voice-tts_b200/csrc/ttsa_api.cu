@@ -586,7 +586,7 @@ extern "C" int ttsa_istft(const ttsa_plan* plan, const ttsa_batch* batch, const 
   if (!stft_dev || !wav_out_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
   DeviceGuard guard(plan->device);
   FrameArgs a{};
-  a.cplx_in = stft_dev; a.wav_out = wav_out_dev;
+  a.cplx_in = stft_dev; a.wav_out = wav_out_dev; a.rows_total = batch->total_frames;
   return launch_frames(plan, batch, MODE_SYNTH, SRC_COMPLEX, false, a, (cudaStream_t)stream);
 }
 
@@ -665,7 +665,8 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
   if (sc_log_dev && iters > 0) CUDA_TRY(cudaMemsetAsync(sc_log_dev, 0, (size_t)iters * batch->B * 2 * 4, st));
 
   FrameArgs a{};
-  a.spec = spec_dev; a.angles = init_angles_dev; a.seed = seed; a.wav_out = bufs[0];
+  a.spec = spec_dev; a.spec_end = spec_dev + (size_t)batch->total_frames * kF; a.rows_total = batch->total_frames;
+  a.angles = init_angles_dev; a.seed = seed; a.wav_out = bufs[0];
   if (int rc = launch_frames(plan, batch, MODE_SYNTH, spec_kind, false, a, st)) return rc;
   for (int i = 1; i <= iters; ++i) {
     FrameArgs b{};
