@@ -372,6 +372,7 @@ def main():
             traffic = None
     roofline = {"kernel": "frame_kernel<MODE_GL_ITER> (one Griffin-Lim iteration over the batch)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                "frac_of_nominal_8tbs": achieved / 8000.0,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": iter_ms,
                 "share_of_step": ITERS * iter_ms / ms_per_step,
                 "init_synthesis_ms": t_init}
@@ -387,8 +388,10 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
+        v1, dt1 = cpu_reference_run(1, 1)            # one utterance on one host thread (the reference's own use)
         v, dt = cpu_reference_run(cores, cores)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "single_thread_value": v1, "single_thread_s_per_utterance": dt1,
                                 "sample": "%d utterances (one per host thread) x inv_mel_spectrogram %d iters, %.1f s wall" % (cores, ITERS, dt)}
     if rank == 0:
         print(json.dumps(line))

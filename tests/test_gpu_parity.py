@@ -353,3 +353,25 @@ def test_host_pipeline_matches_direct_calls():
         for u in range(len(Ts)):
             a, b = lay.split_wav(outs[i])[u], lay.split_wav(ref)[u]
             assert torch.equal(a, b)
+
+
+def test_feature_extraction_training_batch_cfg3():
+    """BASELINE configs[2]: spectrogram + melspectrogram of a 32-utterance batch of 6 s waves in one pass."""
+    ap, orc = _ap(MAIN_AUDIO), OracleAudioProcessor(**MAIN_AUDIO)
+    B, n = 32, 132300
+    waves = [synth_speech_like(2000 + i, n_samples=n) for i in (0, 17)]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    packed = torch.randn((B, n), device="cuda", generator=g) * 0.1
+    packed[0] = torch.from_numpy(waves[0]).cuda()
+    packed[17] = torch.from_numpy(waves[1]).cuda()
+    lay = ap.layout(wav_lengths=[n] * B)
+    assert lay.total_samples == B * n and lay.total_frames == B * 482
+    lin, mel = ap.features_batch(packed.reshape(-1), lay)
+    lin2, mel2 = ap.features_batch(packed.reshape(-1), lay)
+    assert torch.equal(lin, lin2) and torch.equal(mel, mel2)
+    for u, w in zip((0, 17), waves):
+        lo, mo = orc.spectrogram(w).T, orc.melspectrogram(w).T
+        l, m = lay.split_frames(lin)[u].cpu().numpy(), lay.split_frames(mel)[u].cpu().numpy()
+        assert l.shape == (482, 1025) and m.shape == (482, 80)
+        assert np.mean(np.abs(l - lo) <= FWD_TOL) >= 0.995 and np.abs(l - lo).max() < 5e-3
+        assert np.mean(np.abs(m - mo) <= FWD_TOL) >= 0.995 and np.abs(m - mo).max() < 5e-3

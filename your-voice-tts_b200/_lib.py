@@ -79,6 +79,17 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        # a clean checkout: compile the CUDA library in-tree (nvcc, sm_100a); still no non-CUDA path
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("ttsa_build", os.path.join(HERE, "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as exc:          # noqa: BLE001 -- reported below
+            raise RuntimeError("%s is missing and could not be built (%s). There is no CPU or library fallback for "
+                               "the audio hot path." % (LIB_PATH, exc))
+    if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             "%s is missing: build it with `python your-voice-tts_b200/build.py` (or __graft_entry__.build()). "
             "There is no CPU or library fallback for the audio hot path." % LIB_PATH)
