@@ -1,6 +1,6 @@
 import re,csv,collections,sys
 sass, src, raw = sys.argv[1:4]
-exec(open('scratch/sass_lines.py').read().split("tot=sum")[0].replace("sass, ncucsv = sys.argv[1], sys.argv[2]","sass, ncucsv = sys.argv[1], sys.argv[2]").replace("topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40","topn=40"))
+exec(open('tools/sass_lines.py').read().split("tot=sum")[0].replace("sass, ncucsv = sys.argv[1], sys.argv[2]","sass, ncucsv = sys.argv[1], sys.argv[2]").replace("topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40","topn=40"))
 lines=open('your-voice-tts_b200/csrc/frame_kernels.cuh').read().split('\n')
 def find(s): 
     return next(i+1 for i,l in enumerate(lines) if s in l)
