@@ -203,6 +203,42 @@ def test_generic_geometry_kernel_class():
         np.testing.assert_allclose(sc, sco, rtol=SC_RTOL)
 
 
+def test_fixed_and_runtime_geometry_kernels_agree(monkeypatch):
+    """The shipped (hop, win) pairs run kernels with the geometry as compile-time constants; TTSA_GENERIC_GEO=1
+    forces the run-time-geometry kernels of the same class.  Both must meet the oracle bar, on a ragged batch with
+    multi-tile segments; and a class-20 geometry that is not shipped (20 kHz: hop 250, win 1000) runs the latter."""
+    from your_voice_tts_b200 import audio as A
+    for sr in (22050, 16000, 24000, 20000):
+        audio = dict(MAIN_AUDIO, sample_rate=sr, griffin_lim_iters=4, preemphasis=0.97)
+        orc = OracleAudioProcessor(**audio)
+        hop = orc.hop_length
+        ys = [synth_speech_like(5 + i, n_samples=hop * n) for i, n in enumerate((37, 9, 64))]
+        specs_o = [orc.spectrogram(y).astype(np.float32) for y in ys]
+        angs = [(2 * np.pi * np.random.default_rng(i).random(s.shape)).astype(np.float32) for i, s in enumerate(specs_o)]
+        res = {}
+        for generic in ("0", "1"):
+            monkeypatch.setenv("TTSA_GENERIC_GEO", generic)
+            A._PLAN_CACHE.clear()
+            ap = _ap(audio)
+            spec0 = ap.spectrogram(ys[0])
+            assert np.mean(np.abs(spec0 - orc.spectrogram(ys[0])) <= FWD_TOL) >= 0.995
+            lay = ap.layout(n_frames=[s.shape[1] for s in specs_o])
+            dev = torch.device("cuda")
+            packed = lambda xs: torch.from_numpy(np.ascontiguousarray(np.concatenate([x.T for x in xs]))).to(dev)
+            with pytest.raises(ValueError):                  # strided views are refused, not misread
+                ap.inv_spectrogram_batch(packed(specs_o).t(), lay)
+            out, sc = ap.inv_spectrogram_batch(packed(specs_o), lay, init_angles=packed(angs), return_sc=True)
+            res[generic] = [o.cpu().numpy() for o in lay.split_wav(out)]
+            for u, s in enumerate(specs_o):
+                wo, sco = orc.inv_spectrogram(s, init_angles=angs[u], return_sc=True)
+                assert snr_db(wo, res[generic][u]) >= GL_SNR_DB, (sr, generic, u, snr_db(wo, res[generic][u]))
+                np.testing.assert_allclose(sc[:, u].cpu().numpy(), sco, rtol=SC_RTOL)
+        for a, b in zip(res["0"], res["1"]):
+            assert snr_db(a, b) >= 100.0
+    monkeypatch.delenv("TTSA_GENERIC_GEO")
+    A._PLAN_CACHE.clear()
+
+
 def test_device_rng_phases():
     audio = dict(MAIN_AUDIO, griffin_lim_iters=6)
     ap = _ap(audio)

@@ -254,7 +254,15 @@ class AudioProcessor(object):
 
     @staticmethod
     def _ptr(t):
-        return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+        if t is None:
+            return ctypes.c_void_p(0)
+        # the C ABI takes plain dense buffers: refuse strided views instead of reading them as if they were dense
+        if not t.is_cuda or not t.is_contiguous():
+            raise ValueError("expected a contiguous CUDA tensor, got %s strides %s on %s"
+                             % (tuple(t.shape), tuple(t.stride()), t.device))
+        if t.dtype not in (_torch().float32, _torch().uint8):
+            raise ValueError("expected a float32 tensor, got %s" % t.dtype)
+        return ctypes.c_void_p(t.data_ptr())
 
     def _to_dev(self, x, dtype=None):
         torch = _torch()

@@ -15,19 +15,45 @@ constexpr int kRowFloats = 68;       // row stride of the 32x32 exchange buffer:
 constexpr int kBufFloats = 32 * kRowFloats;       // per-warp exchange buffer, reused as the warp's overlap-add slot
 constexpr int kSlotPlane = 1040;     // slot = even-sample plane + odd-sample plane (16 banks apart)
 
+// Shared-memory layout and derived lengths of a (hop, win) geometry in kernel class `nz` (float offsets).  One
+// constexpr function serves the host (plan creation) and the kernels: the shipped geometries are instantiated with
+// compile-time (hop, win), so every offset, bound and stride below folds into an immediate; any other geometry
+// runs the same code with the values read from Geo.
+struct Layout {
+  int hop, win, off0, half, wlen, plane_len, carry_len, span_len, nwarm;
+  int sm_plane0, sm_plane1, sm_carry0, sm_wE, sm_wO, sm_pw, sm_wsyn, sm_tw, sm_g, sm_total;
+};
+__host__ __device__ constexpr int round_up_c(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ constexpr Layout make_layout(int hop, int win, int nz) {
+  Layout l{};
+  l.hop = hop;
+  l.win = win;
+  l.off0 = kNfft / 2 - (kNfft - win) / 2;
+  l.half = (win + 1) / 2;
+  l.wlen = nz * 32;
+  l.carry_len = win - hop;
+  l.span_len = (kNF - 1) * hop + win;
+  l.nwarm = (win - 1) / hop;
+  int off = kNF * kBufFloats;
+  // a frame's loads start at up to ((kNF-1)*hop + 1)/2 and reach nz*32 packed samples further (zero tail)
+  l.plane_len = round_up_c(((kNF - 1) * hop + 1) / 2 + 1 + nz * 32, 32);
+  l.sm_plane0 = off; off += l.plane_len + 16;     // plane1 starts 16 banks away from plane0
+  l.sm_plane1 = off; off += l.plane_len;
+  l.sm_carry0 = off; off += round_up_c(l.carry_len + 1, 4);
+  l.sm_wE = off; off += l.wlen;
+  l.sm_wO = off; off += l.wlen;
+  l.sm_pw = off; off += round_up_c(hop, 4);
+  l.sm_wsyn = off; off += round_up_c(win, 4);
+  l.sm_tw = off; off += 2048;
+  l.sm_g = off; off += 1024;
+  l.sm_total = off;
+  return l;
+}
+
 // Geometry and scalar constants, passed by value to every frame kernel.
 struct Geo {
-  int hop, win, off0;        // off0 = n_fft/2 - (n_fft - win)/2: sample offset of window tap 0 relative to t*hop
-  int half;                  // ceil(win / 2): number of packed complex inputs that are not identically zero
-  int wlen;                  // floats in each paired window table held in shared memory (kernel class rows * 32)
-  int plane_len;             // floats in each parity plane of the staged span (tail beyond the span stays zero)
-  int carry_len;             // win - hop
-  int span_len;              // (kNF-1)*hop + win
-  int nwarm;                 // (win-1)/hop: earlier frames overlapping a segment's first owned sample
+  Layout ly;
   int num_mels;
-  float inv_hop;
-  // shared memory layout (float offsets)
-  int sm_plane0, sm_plane1, sm_carry0, sm_carry1, sm_wE, sm_wO, sm_pw, sm_wsyn, sm_tw, sm_g, sm_total;
   // spectrogram value -> magnitude:  S = exp2(c1 * clip(x, lo, hi) + c0)   (denormalize, +ref, db_to_amp, **power fused)
   float s_c1, s_c0, s_lo, s_hi;
   // amplitude -> normalised dB:      v = clip(n_a * log2(max(min_amp, a)) + n_b, n_lo, n_hi)

@@ -5,17 +5,14 @@ namespace ttsa {
 
 const char* configure_analysis(size_t smem_bytes) {
   const char* e;
-  if ((e = set_smem(frame_kernel<MODE_ANALYSIS, OUT_COMPLEX, 20, false>, smem_bytes))) return e;
-  if ((e = set_smem(frame_kernel<MODE_ANALYSIS, OUT_COMPLEX, 32, false>, smem_bytes))) return e;
-  if ((e = set_smem(frame_kernel<MODE_ANALYSIS, OUT_FEATURES, 20, false>, smem_bytes))) return e;
-  if ((e = set_smem(frame_kernel<MODE_ANALYSIS, OUT_FEATURES, 32, false>, smem_bytes))) return e;
-  return nullptr;
+  if ((e = configure_variants<MODE_ANALYSIS, OUT_COMPLEX, false>(smem_bytes))) return e;
+  return configure_variants<MODE_ANALYSIS, OUT_FEATURES, false>(smem_bytes);
 }
 
-const char* launch_analysis(int out, int nz, int grid, size_t smem, cudaStream_t st, const Geo& g, const Tables& tb,
+const char* launch_analysis(int out, int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo& g, const Tables& tb,
                             const BatchDev& bd, const FrameArgs& a) {
-  if (out == OUT_COMPLEX) { if (nz == 20) TTSA_LAUNCH((frame_kernel<MODE_ANALYSIS, OUT_COMPLEX, 20, false>)); else TTSA_LAUNCH((frame_kernel<MODE_ANALYSIS, OUT_COMPLEX, 32, false>)); }
-  else                    { if (nz == 20) TTSA_LAUNCH((frame_kernel<MODE_ANALYSIS, OUT_FEATURES, 20, false>)); else TTSA_LAUNCH((frame_kernel<MODE_ANALYSIS, OUT_FEATURES, 32, false>)); }
+  if (out == OUT_COMPLEX) return launch_variant<MODE_ANALYSIS, OUT_COMPLEX, false>(nz, fixed, grid, smem, st, g, tb, bd, a);
+  return launch_variant<MODE_ANALYSIS, OUT_FEATURES, false>(nz, fixed, grid, smem, st, g, tb, bd, a);
 }
 
 const char* configure_frame_kernels(size_t smem_bytes, int* ctas_per_sm) {
@@ -25,11 +22,11 @@ const char* configure_frame_kernels(size_t smem_bytes, int* ctas_per_sm) {
   return configure_analysis(smem_bytes);
 }
 
-const char* launch_frame_kernel(int mode, int src, int nz, bool sc, int grid, size_t smem_bytes, cudaStream_t st,
+const char* launch_frame_kernel(int mode, int src, int nz, bool sc, bool fixed, int grid, size_t smem_bytes, cudaStream_t st,
                                 const Geo& g, const Tables& tb, const BatchDev& bd, const FrameArgs& a) {
-  if (mode == MODE_GL_ITER) return launch_gl(src, nz, sc, grid, smem_bytes, st, g, tb, bd, a);
-  if (mode == MODE_SYNTH) return launch_synth(src, nz, grid, smem_bytes, st, g, tb, bd, a);
-  return launch_analysis(src, nz, grid, smem_bytes, st, g, tb, bd, a);
+  if (mode == MODE_GL_ITER) return launch_gl(src, nz, sc, fixed, grid, smem_bytes, st, g, tb, bd, a);
+  if (mode == MODE_SYNTH) return launch_synth(src, nz, fixed, grid, smem_bytes, st, g, tb, bd, a);
+  return launch_analysis(src, nz, fixed, grid, smem_bytes, st, g, tb, bd, a);
 }
 
 }  // namespace ttsa

@@ -144,10 +144,14 @@ __device__ __forceinline__ float2 shfl2(float a, float b, int srclane) {
   return make_float2(__shfl_sync(0xffffffffu, a, srclane), __shfl_sync(0xffffffffu, b, srclane));
 }
 
-template <int MODE, int SRC, int NZ, bool SC>
+// HOP, WIN > 0: geometry fixed at compile time (the shipped configurations); 0: read from Geo at run time.
+template <int MODE, int SRC, int NZ, bool SC, int HOP = 0, int WIN = 0>
 __global__ void __launch_bounds__(kThreads, 2)
 frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a) {
   extern __shared__ __align__(16) float smem[];
+  constexpr bool kFixed = HOP > 0;
+  constexpr Layout kLy = make_layout(kFixed ? HOP : 256, kFixed ? WIN : 1024, NZ);
+  const Layout ly = kFixed ? kLy : g.ly;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr float kInvN = 1.0f / (float)kNfft;
   constexpr float kTiny = 1e-37f;
@@ -159,27 +163,27 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
                                                   // for every shipped geometry; any remainder is copied synchronously)
 
   float* const buf = smem + warp * kBufFloats;
-  float* const plane0 = smem + g.sm_plane0;
-  float* const plane1 = smem + g.sm_plane1;
-  float* const carry = smem + g.sm_carry0;
-  const float2* const wE2 = reinterpret_cast<const float2*>(smem + g.sm_wE);
-  const float2* const wO2 = reinterpret_cast<const float2*>(smem + g.sm_wO);
-  float* const pw = smem + g.sm_pw;
-  float* const wsyn = smem + g.sm_wsyn;         // synthesis window per tap, odd taps negated (conjugate-FFT inverse)
-  const float4* const tw4 = reinterpret_cast<const float4*>(smem + g.sm_tw);
-  const float4* const g4 = reinterpret_cast<const float4*>(smem + g.sm_g);
+  float* const plane0 = smem + ly.sm_plane0;
+  float* const plane1 = smem + ly.sm_plane1;
+  float* const carry = smem + ly.sm_carry0;
+  const float2* const wE2 = reinterpret_cast<const float2*>(smem + ly.sm_wE);
+  const float2* const wO2 = reinterpret_cast<const float2*>(smem + ly.sm_wO);
+  float* const pw = smem + ly.sm_pw;
+  float* const wsyn = smem + ly.sm_wsyn;         // synthesis window per tap, odd taps negated (conjugate-FFT inverse)
+  const float4* const tw4 = reinterpret_cast<const float4*>(smem + ly.sm_tw);
+  const float4* const g4 = reinterpret_cast<const float4*>(smem + ly.sm_g);
 
   // plan tables -> shared memory (once per persistent CTA); staged-span planes start zeroed (their tails stay zero)
-  for (int i = tid; i < 512; i += kThreads) reinterpret_cast<float4*>(smem + g.sm_tw)[i] = tb.tw4[i];
-  for (int i = tid; i < 256; i += kThreads) reinterpret_cast<float4*>(smem + g.sm_g)[i] = tb.g4[i];
-  for (int i = tid; i < g.wlen / 2; i += kThreads) {
-    reinterpret_cast<float2*>(smem + g.sm_wE)[i] = tb.wE2[i];
-    reinterpret_cast<float2*>(smem + g.sm_wO)[i] = tb.wO2[i];
+  for (int i = tid; i < 512; i += kThreads) reinterpret_cast<float4*>(smem + ly.sm_tw)[i] = tb.tw4[i];
+  for (int i = tid; i < 256; i += kThreads) reinterpret_cast<float4*>(smem + ly.sm_g)[i] = tb.g4[i];
+  for (int i = tid; i < ly.wlen / 2; i += kThreads) {
+    reinterpret_cast<float2*>(smem + ly.sm_wE)[i] = tb.wE2[i];
+    reinterpret_cast<float2*>(smem + ly.sm_wO)[i] = tb.wO2[i];
   }
-  for (int i = tid; i < g.plane_len; i += kThreads) { plane0[i] = 0.0f; plane1[i] = 0.0f; }
+  for (int i = tid; i < ly.plane_len; i += kThreads) { plane0[i] = 0.0f; plane1[i] = 0.0f; }
   if constexpr (MODE != MODE_ANALYSIS) {
-    for (int i = tid; i < g.hop; i += kThreads) pw[i] = tb.pw[i] * kInvN;     // 1/wss and the 1/n_fft of the inverse FFT
-    for (int i = tid; i < g.win; i += kThreads) wsyn[i] = (i & 1) ? -tb.wO[i >> 1] : tb.wE[i >> 1];
+    for (int i = tid; i < ly.hop; i += kThreads) pw[i] = tb.pw[i] * kInvN;     // 1/wss and the 1/n_fft of the inverse FFT
+    for (int i = tid; i < ly.win; i += kThreads) wsyn[i] = (i & 1) ? -tb.wO[i >> 1] : tb.wE[i >> 1];
   }
 
   // programmatic dependent launch: let the next kernel on the stream begin its prologue, and wait here until the
@@ -216,8 +220,8 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     const float* __restrict__ src = (MODE != MODE_SYNTH) ? a.wav_in + woff : nullptr;
 
     // frames of earlier tiles still overlap this segment's first owned sample: recompute them (no output)
-    const bool warm = (MODE != MODE_ANALYSIS) && ja > 0 && g.nwarm > 0;
-    const int first_needed = warm ? ja * kNF - g.nwarm : 0;
+    const bool warm = (MODE != MODE_ANALYSIS) && ja > 0 && ly.nwarm > 0;
+    const int first_needed = warm ? ja * kNF - ly.nwarm : 0;
     const int jt_first = warm ? ja - 1 : ja;
     bool has_carry = false;
     float sc_num = 0.0f, sc_den = 0.0f;
@@ -226,14 +230,14 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     //      re/im frame loads are conflict-free
     float stg[kStage];
     auto stage_load = [&](int jt) {
-      const int i0 = jt * kNF * g.hop - g.off0;
-      if (i0 >= 1 && i0 + g.span_len <= L) {                       // interior span: no reflection
+      const int i0 = jt * kNF * ly.hop - ly.off0;
+      if (i0 >= 1 && i0 + ly.span_len <= L) {                       // interior span: no reflection
         const float* __restrict__ sp = src + i0;
 #pragma unroll
         for (int e = 0; e < kStage; ++e) {
           const int s = tid + e * kThreads;
           float val = 0.0f;
-          if (s < g.span_len) {
+          if (s < ly.span_len) {
             val = __ldg(sp + s);
             if (MODE == MODE_ANALYSIS && a.preemph) val = fmaf(-g.preemph, __ldg(sp + s - 1), val);
           }
@@ -244,7 +248,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         for (int e = 0; e < kStage; ++e) {
           const int s = tid + e * kThreads;
           float val = 0.0f;
-          if (s < g.span_len) {
+          if (s < ly.span_len) {
             const int j = reflect_index(i0 + s, L);
             val = __ldg(src + j);
             if (MODE == MODE_ANALYSIS && a.preemph) val = fmaf(-g.preemph, j > 0 ? __ldg(src + j - 1) : 0.0f, val);
@@ -257,9 +261,9 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
       float* const pl = ((tid & 1) ? plane1 : plane0) + (tid >> 1);    // parity of tid + e*kThreads = parity of tid
 #pragma unroll
       for (int e = 0; e < kStage; ++e)
-        if (tid + e * kThreads < g.span_len) pl[e * (kThreads / 2)] = stg[e];
-      const int i0 = jt * kNF * g.hop - g.off0;
-      for (int s = tid + kStage * kThreads; s < g.span_len; s += kThreads) {     // spans longer than the register window
+        if (tid + e * kThreads < ly.span_len) pl[e * (kThreads / 2)] = stg[e];
+      const int i0 = jt * kNF * ly.hop - ly.off0;
+      for (int s = tid + kStage * kThreads; s < ly.span_len; s += kThreads) {     // spans longer than the register window
         const int j = reflect_index(i0 + s, L);
         float val = __ldg(src + j);
         if (MODE == MODE_ANALYSIS && a.preemph) val = fmaf(-g.preemph, j > 0 ? __ldg(src + j - 1) : 0.0f, val);
@@ -276,14 +280,14 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
 
     for (int jt = jt_first; jt < jb; ++jt) {
       const int t0 = jt * kNF;
-      const int i0 = t0 * g.hop - g.off0;        // sample index of span position 0
+      const int i0 = t0 * ly.hop - ly.off0;        // sample index of span position 0
       const bool write_out = jt >= ja;
 
       if constexpr (MODE != MODE_SYNTH) {
         // pull the next tile's span towards L2 while this tile is being transformed
         if (jt + 1 < jb) {
-          const int pi = (jt + 1) * kNF * g.hop - g.off0 + tid * 32;
-          if (pi >= 0 && pi < L && tid * 32 < g.span_len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + pi));
+          const int pi = (jt + 1) * kNF * ly.hop - ly.off0 + tid * 32;
+          if (pi >= 0 && pi < L && tid * 32 < ly.span_len) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + pi));
         }
       }
       const int t = t0 + warp;
@@ -297,7 +301,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         constexpr int kHalfEnd = (MODE == MODE_ANALYSIS) ? 1 : 2;
         const int partner = (32 - lane) & 31;
         const bool l0 = lane == 0;
-        const int lpad = (kNfft - g.win) >> 1;
+        const int lpad = (kNfft - ly.win) >> 1;
 
 #pragma unroll 1
         for (int half = kHalfBegin; half < kHalfEnd; ++half) {
@@ -306,7 +310,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
             // element n2 of this lane is z[lane + 32 n2] = x[2q] + j x[2q+1], q = lane + 32 n2; rows past the
             // window read zero window taps (the planes' tails are zero, so the products are exact zeros)
             if constexpr (MODE != MODE_SYNTH) {
-              const int o = warp * g.hop;
+              const int o = warp * ly.hop;
               const float* re_p = ((o & 1) ? plane1 + ((o - 1) >> 1) : plane0 + (o >> 1)) + lane;
               const float* im_p = ((o & 1) ? plane0 + ((o + 1) >> 1) : plane1 + (o >> 1)) + lane;
 #pragma unroll
@@ -594,8 +598,8 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
           for (int m = 0; m < 16; ++m) {
             if (2 * m < NZ) {
               const int q = lane + 64 * m;
-              if (q < g.half) { buf[q] = R[m].x; buf[kSlotPlane + q] = I[m].x; }
-              if (q + 32 < g.half) { buf[q + 32] = R[m].y; buf[kSlotPlane + q + 32] = I[m].y; }
+              if (q < ly.half) { buf[q] = R[m].x; buf[kSlotPlane + q] = I[m].x; }
+              if (q + 32 < ly.half) { buf[q + 32] = R[m].y; buf[kSlotPlane + q + 32] = I[m].y; }
             }
           }
         }
@@ -618,20 +622,20 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         const int fv_lo = first_needed > t0 ? first_needed - t0 : 0;
         const int fv_hi = (T - t0) < kNF ? (T - t0) : kNF;
         // the utterance's last tile also flushes what would be its carry (samples up to hop*(T-1) end there)
-        const int out_len = (t0 + kNF >= T) ? g.span_len : kNF * g.hop;
+        const int out_len = (t0 + kNF >= T) ? ly.span_len : kNF * ly.hop;
         float* __restrict__ dst = a.wav_out + woff;
         const bool interior = write_out && fv_lo == 0 && fv_hi == kNF && i0 >= 0 && t0 + kNF < T &&
-                              i0 + kNF * g.hop <= L && t0 >= ND - 1;
+                              i0 + kNF * ly.hop <= L && t0 >= ND - 1;
         // finished sample `val` at span position sidx = j*hop + rr: scale and store, or keep as carry
         auto emit = [&](int j, int rr, int sidx, float val) {
-          if (sidx >= g.span_len) return;
+          if (sidx >= ly.span_len) return;
           if (sidx < out_len) {
             const int i = i0 + sidx;
             if (write_out && i >= 0 && i < L) {
               float inv = pw[rr];
-              if (t0 + j - (g.win - 1 - rr) / g.hop < 0 || t0 + j > T - 1) {   // some overlapping frame does not exist
+              if (t0 + j - (ly.win - 1 - rr) / ly.hop < 0 || t0 + j > T - 1) {   // some overlapping frame does not exist
                 float ws = 0.0f;
-                for (int d = 0, m = rr; m < g.win; ++d, m += g.hop) {
+                for (int d = 0, m = rr; m < ly.win; ++d, m += ly.hop) {
                   const int tt = t0 + j - d;
                   if (tt >= 0 && tt < T) ws = fmaf(wsyn[m], wsyn[m], ws);
                 }
@@ -643,21 +647,21 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
             carry[sidx - out_len] = val;
           }
         };
-        if (tid < g.hop && !(a.debug & 2)) {
+        if (tid < ly.hop && !(a.debug & 2)) {
           const int rr = tid;
           float acc[kNF + ND - 1];
           float wreg[ND];
           int off[ND];
 #pragma unroll
           for (int d = 0; d < ND; ++d) {
-            const int m = rr + d * g.hop;                 // window tap; odd taps carry the conjugation sign
-            wreg[d] = m < g.win ? wsyn[m] : 0.0f;
-            off[d] = m < g.win ? ((m & 1) ? kSlotPlane : 0) + (m >> 1) : 0;
+            const int m = rr + d * ly.hop;                 // window tap; odd taps carry the conjugation sign
+            wreg[d] = m < ly.win ? wsyn[m] : 0.0f;
+            off[d] = m < ly.win ? ((m & 1) ? kSlotPlane : 0) + (m >> 1) : 0;
           }
 #pragma unroll
           for (int j = 0; j < kNF + ND - 1; ++j) {
-            const int sidx = j * g.hop + rr;
-            acc[j] = (has_carry && j < ND - 1 && sidx < g.carry_len) ? carry[sidx] : 0.0f;
+            const int sidx = j * ly.hop + rr;
+            acc[j] = (has_carry && j < ND - 1 && sidx < ly.carry_len) ? carry[sidx] : 0.0f;
           }
 #pragma unroll
           for (int f = 0; f < kNF; ++f) {
@@ -670,11 +674,11 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
           if (interior) {
             const float inv = pw[rr];
 #pragma unroll
-            for (int j = 0; j < kNF; ++j) dst[i0 + j * g.hop + rr] = acc[j] * inv;
+            for (int j = 0; j < kNF; ++j) dst[i0 + j * ly.hop + rr] = acc[j] * inv;
 #pragma unroll
             for (int j = kNF; j < kNF + ND - 1; ++j) {
-              const int c = (j - kNF) * g.hop + rr;
-              if (c < g.carry_len) carry[c] = acc[j];
+              const int c = (j - kNF) * ly.hop + rr;
+              if (c < ly.carry_len) carry[c] = acc[j];
             }
           } else {
 #pragma unroll 1
@@ -682,20 +686,20 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               float val = 0.0f;
 #pragma unroll
               for (int jj = 0; jj < kNF + ND - 1; ++jj) val = (jj == j) ? acc[jj] : val;
-              emit(j, rr, j * g.hop + rr, val);
+              emit(j, rr, j * ly.hop + rr, val);
             }
           }
         }
         // residues beyond the thread count (hop 275 = 256 + 19): one small item per (residue, j mod kNF) spread over
         // all warps, instead of a second full round that only a few lanes of one warp would execute
-        if (g.hop > kThreads && !(a.debug & 2)) {
-          const int nl = g.hop - kThreads;
+        if (ly.hop > kThreads && !(a.debug & 2)) {
+          const int nl = ly.hop - kThreads;
           for (int it = tid; it < nl * kNF; it += kThreads) {
             const int jl = it / nl, rr = kThreads + it - jl * nl;
-            const int sa = jl * g.hop + rr, sb = sa + kNF * g.hop;
-            float va = (has_carry && sa < g.carry_len) ? carry[sa] : 0.0f;
+            const int sa = jl * ly.hop + rr, sb = sa + kNF * ly.hop;
+            float va = (has_carry && sa < ly.carry_len) ? carry[sa] : 0.0f;
             float vb = 0.0f;
-            for (int d = 0, m = rr; d < ND && m < g.win; ++d, m += g.hop) {
+            for (int d = 0, m = rr; d < ND && m < ly.win; ++d, m += ly.hop) {
               const int po = ((m & 1) ? kSlotPlane : 0) + (m >> 1);
               const float w = wsyn[m];
               const int fa = jl - d, fb = fa + kNF;

@@ -5,20 +5,16 @@ namespace ttsa {
 
 const char* configure_synth(size_t smem_bytes) {
   const char* e;
-  if ((e = set_smem(frame_kernel<MODE_SYNTH, SRC_MAG, 20, false>, smem_bytes))) return e;
-  if ((e = set_smem(frame_kernel<MODE_SYNTH, SRC_MAG, 32, false>, smem_bytes))) return e;
-  if ((e = set_smem(frame_kernel<MODE_SYNTH, SRC_NORM_DB, 20, false>, smem_bytes))) return e;
-  if ((e = set_smem(frame_kernel<MODE_SYNTH, SRC_NORM_DB, 32, false>, smem_bytes))) return e;
-  if ((e = set_smem(frame_kernel<MODE_SYNTH, SRC_COMPLEX, 20, false>, smem_bytes))) return e;
-  if ((e = set_smem(frame_kernel<MODE_SYNTH, SRC_COMPLEX, 32, false>, smem_bytes))) return e;
-  return nullptr;
+  if ((e = configure_variants<MODE_SYNTH, SRC_MAG, false>(smem_bytes))) return e;
+  if ((e = configure_variants<MODE_SYNTH, SRC_NORM_DB, false>(smem_bytes))) return e;
+  return configure_variants<MODE_SYNTH, SRC_COMPLEX, false>(smem_bytes);
 }
 
-const char* launch_synth(int src, int nz, int grid, size_t smem, cudaStream_t st, const Geo& g, const Tables& tb,
+const char* launch_synth(int src, int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo& g, const Tables& tb,
                          const BatchDev& bd, const FrameArgs& a) {
-  if (src == SRC_MAG)          { if (nz == 20) TTSA_LAUNCH((frame_kernel<MODE_SYNTH, SRC_MAG, 20, false>)); else TTSA_LAUNCH((frame_kernel<MODE_SYNTH, SRC_MAG, 32, false>)); }
-  else if (src == SRC_NORM_DB) { if (nz == 20) TTSA_LAUNCH((frame_kernel<MODE_SYNTH, SRC_NORM_DB, 20, false>)); else TTSA_LAUNCH((frame_kernel<MODE_SYNTH, SRC_NORM_DB, 32, false>)); }
-  else                         { if (nz == 20) TTSA_LAUNCH((frame_kernel<MODE_SYNTH, SRC_COMPLEX, 20, false>)); else TTSA_LAUNCH((frame_kernel<MODE_SYNTH, SRC_COMPLEX, 32, false>)); }
+  if (src == SRC_MAG) return launch_variant<MODE_SYNTH, SRC_MAG, false>(nz, fixed, grid, smem, st, g, tb, bd, a);
+  if (src == SRC_NORM_DB) return launch_variant<MODE_SYNTH, SRC_NORM_DB, false>(nz, fixed, grid, smem, st, g, tb, bd, a);
+  return launch_variant<MODE_SYNTH, SRC_COMPLEX, false>(nz, fixed, grid, smem, st, g, tb, bd, a);
 }
 
 }  // namespace ttsa

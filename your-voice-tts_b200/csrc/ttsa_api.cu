@@ -12,7 +12,6 @@
 #include "../../include/ttsa.h"
 #include "aux_kernels.cuh"
 #include "frame_launch.cuh"
-#include "gl_chain.cuh"
 #include "host_tables.hpp"
 #include "mel_gemm_tc.cuh"
 
@@ -64,9 +63,7 @@ struct ttsa_plan {
   std::vector<double> h_inv_mel;   // [F][num_mels]
   int nz = 32;                     // compile-time zero-pruning class of the frame kernels (20 or 32)
   int ctas_per_sm = 1;
-  bool use_chain = false;          // Griffin-Lim iterations run the barrier-free warp-chain kernel (standard class)
-  ChainSmem chain_sm;
-  int chain_ctas_per_sm = 1;
+  bool fixed_geo = true;           // use the kernels compiled for this (hop, win) when they exist (TTSA_GENERIC_GEO=1: never)
   // device allocations
   void* d_block = nullptr;         // one allocation holding every table
   const float* d_pinvT = nullptr;  // [num_mels][ldp]
@@ -114,36 +111,9 @@ static int kernel_class(const ttsa_config& c) {
 static int build_geo(const ttsa_config& c, Geo& g) {
   const int nz = kernel_class(c);
   std::memset(&g, 0, sizeof(g));
-  g.hop = c.hop_length;
-  g.win = c.win_length;
-  const int lpad = (kNfft - c.win_length) / 2;
-  g.off0 = kNfft / 2 - lpad;
-  g.half = (c.win_length + 1) / 2;
-  g.wlen = nz * 32;
-  g.carry_len = c.win_length - c.hop_length;
-  g.span_len = (kNF - 1) * c.hop_length + c.win_length;
-  g.nwarm = (c.win_length - 1) / c.hop_length;
+  g.ly = make_layout(c.hop_length, c.win_length, nz);
   g.num_mels = c.num_mels;
-  g.inv_hop = 1.0f / (float)c.hop_length;
   g.preemph = (float)c.preemphasis;
-  // shared memory layout
-  int off = kNF * kBufFloats;
-  // a frame's loads start at up to ((kNF-1)*hop + 1)/2 and reach nz*32 packed samples further (zero tail)
-  const int plane_len = round_up(((kNF - 1) * c.hop_length + 1) / 2 + 1 + nz * 32, 32);
-  g.plane_len = plane_len;
-  g.sm_plane0 = off;
-  off += plane_len + 16;                        // plane1 starts 16 banks away from plane0
-  g.sm_plane1 = off;
-  off += plane_len;
-  g.sm_carry0 = off; off += round_up(g.carry_len + 1, 4);
-  g.sm_carry1 = g.sm_carry0;
-  g.sm_wE = off; off += g.wlen;
-  g.sm_wO = off; off += g.wlen;
-  g.sm_pw = off; off += round_up(g.hop, 4);
-  g.sm_wsyn = off; off += round_up(g.win, 4);
-  g.sm_tw = off; off += 2048;
-  g.sm_g = off; off += 1024;
-  g.sm_total = off;
 
   // value conversions (utils/audio.py:79-126)
   const double LOG2_10 = std::log2(10.0);
@@ -235,9 +205,9 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->device = device;
   build_geo(c, p->geo);
   p->nz = kernel_class(c);
-  if ((size_t)p->geo.sm_total * 4 > 227 * 1024) {
+  if ((size_t)p->geo.ly.sm_total * 4 > 227 * 1024) {
     delete p;
-    return fail(TTSA_ERR_UNSUPPORTED, "hop/win need %d bytes of shared memory per CTA", p->geo.sm_total * 4);
+    return fail(TTSA_ERR_UNSUPPORTED, "hop/win need %d bytes of shared memory per CTA", p->geo.ly.sm_total * 4);
   }
 
   // ---- host tables (float64) ----
@@ -368,30 +338,12 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->d_pinvT = (const float*)(base + pieces[8].off);
 
   // configure every kernel once (dynamic shared memory opt-in, occupancy), outside any stream capture
-  const size_t smem_bytes = (size_t)p->geo.sm_total * 4;
+  const size_t smem_bytes = (size_t)p->geo.ly.sm_total * 4;
   int occ = 0;
   const char* err = configure_frame_kernels(smem_bytes, &occ);
   if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
   p->ctas_per_sm = occ < 1 ? 1 : occ;
-  if (p->nz == 20 && c.win_length + (kNF - 1) * c.hop_length <= kAccLen) {
-    ChainSmem& cs = p->chain_sm;
-    int off = kNF * kBufFloats;
-    cs.acc = off; off += 2 * kAccPlane;
-    cs.wE = off; off += 20 * 32;
-    cs.wO = off; off += 20 * 32;
-    cs.pw = off; off += round_up(c.hop_length, 4);
-    cs.tw = off; off += 2048;
-    cs.g = off; off += 1024;
-    cs.total = off;
-    int occ2 = 0;
-    err = configure_gl_chain((size_t)cs.total * 4, &occ2);
-    if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "chain kernel configuration: %s", err); }
-    p->chain_ctas_per_sm = occ2 < 1 ? 1 : occ2;
-    // Experimental: measured slower than the tiled kernel on B200 (0.23 vs 0.20 ms per iteration at 64 x 482 frames:
-    // the strictly ordered adds convoy).  Opt in with TTSA_GL_KERNEL=chain for profiling.
-    const char* sel = std::getenv("TTSA_GL_KERNEL");
-    p->use_chain = sel != nullptr && std::strcmp(sel, "chain") == 0;
-  }
+  { const char* gen = std::getenv("TTSA_GENERIC_GEO"); p->fixed_geo = !(gen != nullptr && std::atoi(gen) != 0); }
   cudaError_t e = cudaFuncSetAttribute(mel_to_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMtlMaxK * (kMtlBins + kMtlRows) * 4);
   if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "mel kernel configuration: %s", cudaGetErrorString(e)); }
@@ -553,8 +505,8 @@ static int launch_frames(const ttsa_plan* plan, const ttsa_batch* batch, int mod
   if (batch->dev.total_tiles == 0) return TTSA_OK;
   const int max_ctas = plan->ctas_per_sm * plan->num_sms;
   const int grid = batch->dev.total_tiles < max_ctas ? batch->dev.total_tiles : max_ctas;
-  const char* err = launch_frame_kernel(mode, src, plan->nz, sc, grid, (size_t)plan->geo.sm_total * 4, st, plan->geo,
-                                        plan->tb, batch->dev, args);
+  const char* err = launch_frame_kernel(mode, src, plan->nz, sc, plan->fixed_geo, grid, (size_t)plan->geo.ly.sm_total * 4, st,
+                                        plan->geo, plan->tb, batch->dev, args);
   if (err) return fail(TTSA_ERR_CUDA, "frame kernel launch (mode %d): %s", mode, err);
   return TTSA_OK;
 }
@@ -675,14 +627,7 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
     b.wav_end = b.wav_in + batch->total_samples;
     { const char* dbg = std::getenv("TTSA_DEBUG"); b.debug = dbg ? std::atoi(dbg) : 0; }
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
-    if (plan->use_chain && batch->dense) {
-      const long long want = (batch->total_frames + kNF - 1) / kNF;
-      const long long max_ctas = (long long)plan->chain_ctas_per_sm * plan->num_sms;
-      const int grid = (int)std::max<long long>(1, std::min(want, max_ctas));
-      const char* err = launch_gl_chain(spec_kind, sc_log_dev != nullptr, grid, (size_t)plan->chain_sm.total * 4, st, plan->geo,
-                                        plan->tb, batch->dev, b, plan->chain_sm, batch->total_frames);
-      if (err) return fail(TTSA_ERR_CUDA, "Griffin-Lim chain kernel launch: %s", err);
-    } else if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st)) {
+    if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st)) {
       return rc;
     }
   }
