@@ -647,40 +647,54 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
             carry[sidx - out_len] = val;
           }
         };
-        if (tid < ly.hop && !(a.debug & 2)) {
-          const int rr = tid;
+        // Residue ownership: warps 0..3 take the even residues 2i, warps 4..7 the odd residues 2i+1 (i = tid mod 128).
+        // Tap m = rr + d*hop of residue rr = 2i + par sits at slot offset i + c(par, d), c = plane(par + d*hop) +
+        // (par + d*hop)/2: a per-thread base plus constants that fold into the load's immediate when the geometry
+        // is fixed at compile time; lanes read consecutive words.
+        auto ola = [&](auto parc) {
+          constexpr int par = decltype(parc)::value;
+          const int i2 = tid & (kThreads / 2 - 1);
+          const int rr = 2 * i2 + par;
+          if (rr >= ly.hop) return;
+          const float* const sl0 = smem + i2;
           float acc[kNF + ND - 1];
           float wreg[ND];
           int off[ND];
 #pragma unroll
           for (int d = 0; d < ND; ++d) {
-            const int m = rr + d * ly.hop;                 // window tap; odd taps carry the conjugation sign
+            const int m = rr + d * ly.hop;                // window tap; odd taps carry the conjugation sign
+            const int e = par + d * ly.hop;
             wreg[d] = m < ly.win ? wsyn[m] : 0.0f;
-            off[d] = m < ly.win ? ((m & 1) ? kSlotPlane : 0) + (m >> 1) : 0;
+            off[d] = m < ly.win ? ((e & 1) ? kSlotPlane : 0) + (e >> 1) : 0;
           }
 #pragma unroll
           for (int j = 0; j < kNF + ND - 1; ++j) {
             const int sidx = j * ly.hop + rr;
             acc[j] = (has_carry && j < ND - 1 && sidx < ly.carry_len) ? carry[sidx] : 0.0f;
           }
-#pragma unroll
-          for (int f = 0; f < kNF; ++f) {
-            if (interior || (f >= fv_lo && f < fv_hi)) {
-              const float* sl = smem + f * kBufFloats;
-#pragma unroll
-              for (int d = 0; d < ND; ++d) acc[f + d] = fmaf(sl[off[d]], wreg[d], acc[f + d]);
-            }
-          }
           if (interior) {
-            const float inv = pw[rr];
 #pragma unroll
-            for (int j = 0; j < kNF; ++j) dst[i0 + j * ly.hop + rr] = acc[j] * inv;
+            for (int f = 0; f < kNF; ++f) {
+#pragma unroll
+              for (int d = 0; d < ND; ++d) acc[f + d] = fmaf(sl0[f * kBufFloats + off[d]], wreg[d], acc[f + d]);
+            }
+            const float inv = pw[rr];
+            float* __restrict__ po = dst + (i0 + rr);
+#pragma unroll
+            for (int j = 0; j < kNF; ++j) po[j * ly.hop] = acc[j] * inv;
 #pragma unroll
             for (int j = kNF; j < kNF + ND - 1; ++j) {
               const int c = (j - kNF) * ly.hop + rr;
               if (c < ly.carry_len) carry[c] = acc[j];
             }
           } else {
+#pragma unroll
+            for (int f = 0; f < kNF; ++f) {
+              if (f >= fv_lo && f < fv_hi) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) acc[f + d] = fmaf(sl0[f * kBufFloats + off[d]], wreg[d], acc[f + d]);
+              }
+            }
 #pragma unroll 1
             for (int j = 0; j < kNF + ND - 1; ++j) {
               float val = 0.0f;
@@ -689,6 +703,10 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               emit(j, rr, j * ly.hop + rr, val);
             }
           }
+        };
+        if (!(a.debug & 2)) {
+          if (tid < kThreads / 2) ola(std::integral_constant<int, 0>{});
+          else ola(std::integral_constant<int, 1>{});
         }
         // residues beyond the thread count (hop 275 = 256 + 19): one small item per (residue, j mod kNF) spread over
         // all warps, instead of a second full round that only a few lanes of one warp would execute
