@@ -15,6 +15,13 @@ constexpr int kRowFloats = 68;       // row stride of the 32x32 exchange buffer:
 constexpr int kBufFloats = 32 * kRowFloats;       // per-warp exchange buffer, reused as the warp's overlap-add slot
 constexpr int kSlotPlane = 1040;     // slot = even-sample plane + odd-sample plane (16 banks apart)
 
+// compile-time integer usable as a generic-lambda argument in device code
+template <int V>
+struct IntC {
+  static constexpr int value = V;
+  __host__ __device__ constexpr operator int() const { return V; }
+};
+
 // Shared-memory layout and derived lengths of a (hop, win) geometry in kernel class `nz` (float offsets).  One
 // constexpr function serves the host (plan creation) and the kernels: the shipped geometries are instantiated with
 // compile-time (hop, win), so every offset, bound and stride below folds into an immediate; any other geometry
