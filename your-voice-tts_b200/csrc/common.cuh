@@ -28,7 +28,8 @@ struct IntC {
 // runs the same code with the values read from Geo.
 struct Layout {
   int hop, win, off0, half, wlen, plane_len, carry_len, span_len, nwarm;
-  int sm_plane0, sm_plane1, sm_carry0, sm_wE, sm_wO, sm_pw, sm_wsyn, sm_tw, sm_g, sm_total;
+  int sm_plane0, sm_plane1, sm_carry0, sm_wE, sm_wO, sm_pw, sm_wsyn, sm_tw, sm_g, sm_mbar, sm_total;
+  int image_floats;          // [sm_wE, sm_mbar): the constant tables, one contiguous image built by the host
 };
 __host__ __device__ constexpr int round_up_c(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ constexpr Layout make_layout(int hop, int win, int nz) {
@@ -53,6 +54,8 @@ __host__ __device__ constexpr Layout make_layout(int hop, int win, int nz) {
   l.sm_wsyn = off; off += round_up_c(win, 4);
   l.sm_tw = off; off += 2048;
   l.sm_g = off; off += 1024;
+  l.image_floats = off - l.sm_wE;                 // a multiple of 4 floats starting on a 16-byte boundary
+  l.sm_mbar = off; off += 4;                      // mbarrier of the table copy
   l.sm_total = off;
   return l;
 }
@@ -77,6 +80,8 @@ struct Tables {
   const float* wE;       // [1024]    w[2q]   (zero padded)
   const float* wO;       // [1024]    w[2q+1]
   const float* pw;       // [hop]    1 / sum_q w[r + q*hop]^2   (interior window-sum-square, periodic in hop)
+  const float* smem_image;  // [Layout::image_floats]  wE2 | wO2 | pw / n_fft | signed synthesis window | tw4 | g4, laid out
+                            // exactly as the kernels keep them in shared memory (one bulk copy per CTA)
   // sparse mel basis (CSR over mel rows; each row is one contiguous run of bins)
   const int* mel_lo;     // [num_mels]
   const int* mel_cnt;    // [num_mels]

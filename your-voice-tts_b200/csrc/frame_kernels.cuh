@@ -174,17 +174,27 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
   const float4* const tw4 = reinterpret_cast<const float4*>(smem + ly.sm_tw);
   const float4* const g4 = reinterpret_cast<const float4*>(smem + ly.sm_g);
 
-  // plan tables -> shared memory (once per persistent CTA); staged-span planes start zeroed (their tails stay zero)
-  for (int i = tid; i < 512; i += kThreads) reinterpret_cast<float4*>(smem + ly.sm_tw)[i] = tb.tw4[i];
-  for (int i = tid; i < 256; i += kThreads) reinterpret_cast<float4*>(smem + ly.sm_g)[i] = tb.g4[i];
-  for (int i = tid; i < ly.wlen / 2; i += kThreads) {
-    reinterpret_cast<float2*>(smem + ly.sm_wE)[i] = tb.wE2[i];
-    reinterpret_cast<float2*>(smem + ly.sm_wO)[i] = tb.wO2[i];
+  // plan tables -> shared memory, once per persistent CTA: ONE bulk asynchronous copy of the host-built image
+  // (paired windows, 1/(N wss), signed synthesis window, twiddles) signalled through an mbarrier, while the threads zero
+  // the staged-span planes (their tails stay zero for the kernel's lifetime)
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem + ly.sm_mbar);
+  if (tid == 0) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem + ly.sm_wE);
+    const unsigned bytes = (unsigned)ly.image_floats * 4u;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(tb.smem_image), "r"(bytes), "r"(mbar) : "memory");
   }
   for (int i = tid; i < ly.plane_len; i += kThreads) { plane0[i] = 0.0f; plane1[i] = 0.0f; }
-  if constexpr (MODE != MODE_ANALYSIS) {
-    for (int i = tid; i < ly.hop; i += kThreads) pw[i] = tb.pw[i] * kInvN;     // 1/wss and the 1/n_fft of the inverse FFT
-    for (int i = tid; i < ly.win; i += kThreads) wsyn[i] = (i & 1) ? -tb.wO[i >> 1] : tb.wE[i >> 1];
+  __syncthreads();                                 // the mbarrier is initialised for everyone
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                   : "=r"(done) : "r"(mbar) : "memory");
+    }
   }
 
   // programmatic dependent launch: let the next kernel on the stream begin its prologue, and wait here until the

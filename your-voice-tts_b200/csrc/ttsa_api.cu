@@ -277,6 +277,17 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     for (int m = r; m < c.win_length; m += c.hop_length) { const double wf = (double)(float)w[m]; acc += wf * wf; }
     h_pw[r] = (float)(1.0 / acc);
   }
+  // shared-memory image of the frame kernels' constant tables (Layout: [sm_wE, sm_mbar))
+  const Layout& ly = p->geo.ly;
+  std::vector<float> h_img(ly.image_floats, 0.f);
+  {
+    float* img = h_img.data() - ly.sm_wE;
+    for (int i = 0; i < ly.wlen; ++i) { img[ly.sm_wE + i] = h_wE2[i]; img[ly.sm_wO + i] = h_wO2[i]; }
+    for (int r = 0; r < c.hop_length; ++r) img[ly.sm_pw + r] = h_pw[r] * (1.0f / (float)kNfft);   // 1/wss and the 1/n_fft of the inverse FFT
+    for (int m = 0; m < c.win_length; ++m) img[ly.sm_wsyn + m] = (m & 1) ? -h_wO[m >> 1] : h_wE[m >> 1];
+    for (int i = 0; i < 2048; ++i) img[ly.sm_tw + i] = h_tw[i];
+    for (int i = 0; i < 1024; ++i) img[ly.sm_g + i] = h_g[i];
+  }
   // banded mel basis
   std::vector<int> h_lo(c.num_mels, 0), h_cnt(c.num_mels, 0);
   int ld = 1;
@@ -309,7 +320,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       {h_cnt.data(), h_cnt.size() * 4, 0}, {h_val.data(), h_val.size() * 4, 0}, {h_pinvT.data(), h_pinvT.size() * 4, 0},
       {h_wE2.data(), h_wE2.size() * 4, 0}, {h_wO2.data(), h_wO2.size() * 4, 0},
       {h_pinv_tc.data(), h_pinv_tc.size() * 2, 0}, {h_mel_tc.data(), h_mel_tc.size() * 2, 0},
-      {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}};
+      {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}, {h_img.data(), h_img.size() * 4, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -328,6 +339,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->d_pinv_tc = (const __nv_bfloat16*)(base + pieces[11].off);
   p->d_mel_tc = h_mel_tc.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[12].off);
   p->d_pinv_tc96 = h_pinv_tc96.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[13].off);
+  p->tb.smem_image = (const float*)(base + pieces[14].off);
   p->tb.wE = (const float*)(base + pieces[2].off);
   p->tb.wO = (const float*)(base + pieces[3].off);
   p->tb.pw = (const float*)(base + pieces[4].off);
