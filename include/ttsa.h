@@ -167,6 +167,29 @@ size_t ttsa_deemphasis_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* 
 int ttsa_deemphasis(const ttsa_plan* plan, const ttsa_batch* batch, const float* x_dev, float* y_dev,
                     void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- waveform post-processing (the steps right after the synthesis path) ------------------ */
+/* max |wav_u| per utterance (the peak save_wav normalises by, utils/audio.py:57).  lens_dev: optional [B] int32
+ * length override (clamped to the batch's lengths), e.g. the endpoints below. */
+int ttsa_wav_peaks(const ttsa_plan* plan, const ttsa_batch* batch, const float* wav_dev, const int32_t* lens_dev,
+                   float* peaks_dev, void* stream);
+/* find_endpoint (utils/audio.py:203-210): window = int(sample_rate * min_silence_sec), hop = int(window / 4); the
+ * first x in range(hop, len - window, hop) whose SIGNED maximum over wav[x : x + window] is below
+ * 10^(threshold_db / 20) gives x + hop, else len.  endpoints_dev: [B] int32. */
+int ttsa_find_endpoint(const ttsa_plan* plan, const ttsa_batch* batch, const float* wav_dev, double threshold_db,
+                       double min_silence_sec, int32_t* endpoints_dev, void* stream);
+/* save_wav's sample conversion (utils/audio.py:56-58): int16(wav * (32767 / max(0.01, max |wav|))), truncating like
+ * numpy's astype.  Utterance u lands at out_off[u] = sum_{v<u} (len_v + gap_samples) followed by gap_samples zeros
+ * (server/synthesizer.py:157-158 appends 10 000 zeros after every sentence and normalises the concatenation by ONE
+ * peak: TTSA_PCM_JOINT_PEAK).  TTSA_PCM_F32_ARITH forms the product in float32 (the reference's arithmetic for a
+ * float32 waveform); the default is float64 (float64 waveform: after de-emphasis, or the server's list).
+ * out_off_dev: [B+1] int64 (out_off[B] = samples written); writes beyond out_capacity samples are dropped. */
+#define TTSA_PCM_JOINT_PEAK 1u
+#define TTSA_PCM_F32_ARITH  2u
+size_t ttsa_pcm16_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* batch);
+int ttsa_wav_to_pcm16(const ttsa_plan* plan, const ttsa_batch* batch, const float* wav_dev, const int32_t* lens_dev,
+                      uint32_t flags, int64_t gap_samples, int64_t* out_off_dev, int16_t* out_dev, int64_t out_capacity,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ---- elementwise steps of the API ------------------------------------------------------- */
 #define TTSA_PW_NORMALIZE   0   /* _normalize    utils/audio.py:79-94   */
 #define TTSA_PW_DENORMALIZE 1   /* _denormalize  utils/audio.py:96-112  */

@@ -385,6 +385,31 @@ class OracleAudioProcessor(object):
             y = self.apply_inv_preemphasis(y)
         return (y, sc) if return_sc else y
 
+    # utils/audio.py:56-58, up to the file write: the int16 samples save_wav hands to scipy.io.wavfile.write
+    def save_wav_int16(self, wav):
+        """float64 waveform (the reference's default path: scipy's lfilter in apply_inv_preemphasis and the server's
+        list concatenation both widen): float64 arithmetic.  float32 waveform: under the reference's pinned numpy
+        (1.14, value-based casting) the scale 32767 / max(0.01, peak) is a float64 scalar and the array product is
+        formed in float32 with that scalar rounded to float32 -- written out explicitly so that the result does not
+        depend on the numpy version running the oracle."""
+        wav = np.asarray(wav)
+        peak = float(np.max(np.abs(wav)))
+        scale = 32767.0 / max(0.01, peak)
+        if wav.dtype == np.float32:
+            wav_norm = wav * np.float32(scale)
+        else:
+            wav_norm = wav.astype(np.float64) * scale
+        return wav_norm.astype(np.int16)
+
+    # server/synthesizer.py:157-161: every sentence is followed by 10 000 zero samples, then ONE save_wav
+    @staticmethod
+    def server_concat(wavs, gap=10000):
+        out = []
+        for w in wavs:
+            out += list(w)
+            out += [0] * gap
+        return np.array(out)
+
     # utils/audio.py:203-210
     def find_endpoint(self, wav, threshold_db=-40, min_silence_sec=0.8):
         window_length = int(self.sample_rate * min_silence_sec)

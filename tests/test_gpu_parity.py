@@ -411,3 +411,95 @@ def test_feature_extraction_training_batch_cfg3():
         assert l.shape == (482, 1025) and m.shape == (482, 80)
         assert np.mean(np.abs(l - lo) <= FWD_TOL) >= 0.995 and np.abs(l - lo).max() < 5e-3
         assert np.mean(np.abs(m - mo) <= FWD_TOL) >= 0.995 and np.abs(m - mo).max() < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ post-processing
+def _packed_wavs(ap, wavs):
+    lay = ap.layout(wav_lengths=[len(w) for w in wavs])
+    buf = torch.zeros((max(1, lay.total_samples),), dtype=torch.float32, device="cuda")
+    for u, w in enumerate(wavs):
+        buf[int(lay.wav_off[u]):int(lay.wav_off[u]) + len(w)] = torch.from_numpy(np.asarray(w, dtype=np.float32)).cuda()
+    return buf, lay
+
+
+def test_pcm16_conversion_bit_exact_vs_oracle():
+    """save_wav's int16 samples (utils/audio.py:56-58): bit-exact against the oracle on the same float32 waveform,
+    in the float64 arithmetic of the reference's default path and in its float32 variant; quiet utterances hit the
+    max(0.01, peak) floor; the server layout (10 000-sample gaps, ONE peak) equals save_wav of the concatenation."""
+    ap, orc = _ap(MAIN_AUDIO), OracleAudioProcessor(**MAIN_AUDIO)
+    rng = np.random.default_rng(5)
+    wavs = [synth_speech_like(40 + i, n_samples=n) * a for i, (n, a) in enumerate([(33000, 1.0), (7001, 0.004), (1, 1.0), (52345, 3.7)])]
+    wavs.append((rng.standard_normal(20000) * 0.3).astype(np.float32))
+    buf, lay = _packed_wavs(ap, wavs)
+    for f32 in (False, True):
+        pcm, off = ap.pcm16_batch(buf, lay, float32_arith=f32)
+        off = off.cpu().numpy()
+        assert off[-1] == sum(len(w) for w in wavs)
+        for u, w in enumerate(wavs):
+            want = orc.save_wav_int16(w if f32 else w.astype(np.float64))
+            got = pcm[off[u]:off[u + 1]].cpu().numpy()
+            assert got.dtype == np.int16 and np.array_equal(got, want), (f32, u, np.abs(got.astype(int) - want).max())
+    pcm, off = ap.pcm16_batch(buf, lay, joint_peak=True, gap_samples=10000)
+    want = orc.save_wav_int16(orc.server_concat([w.astype(np.float64) for w in wavs]))
+    n = int(off[-1].item())
+    assert n == len(want) and np.array_equal(pcm[:n].cpu().numpy(), want)
+    peaks = ap.wav_peaks_batch(buf, lay).cpu().numpy()
+    np.testing.assert_array_equal(peaks, [np.max(np.abs(w)) for w in wavs])
+
+
+def test_find_endpoint_vs_oracle():
+    """find_endpoint (utils/audio.py:203-210) incl. its quirks: the SIGNED maximum is compared, candidates start at
+    hop, utterances shorter than window + hop return their length."""
+    ap, orc = _ap(MAIN_AUDIO), OracleAudioProcessor(**MAIN_AUDIO)
+    rng = np.random.default_rng(9)
+    sr = 22050
+    speech = lambda n, s: synth_speech_like(s, n_samples=n)
+    hush = lambda n: (rng.standard_normal(n) * 0.002).astype(np.float32)
+    wavs = [np.concatenate([speech(int(1.3 * sr), 1), hush(int(1.7 * sr)), speech(sr, 2)]),      # silence in the middle
+            speech(3 * sr, 3),                                                                      # none
+            np.concatenate([speech(sr, 4), hush(3 * sr)]),                                         # trailing silence
+            hush(2 * sr),                                                                           # silent from the start
+            speech(9000, 5),                                                                        # shorter than a window
+            -np.abs(speech(2 * sr, 6)) - 0.1,                                                       # negative-only: "silent" for the reference
+            np.concatenate([speech(int(0.9 * sr), 7), hush(int(0.82 * sr)), speech(sr, 8)])]       # barely long enough
+    buf, lay = _packed_wavs(ap, wavs)
+    got = ap.find_endpoint_batch(buf, lay).cpu().numpy()
+    want = [orc.find_endpoint(w) for w in wavs]
+    assert got.tolist() == want, (got.tolist(), want)
+    assert len(set(want)) >= 5
+    got2 = ap.find_endpoint_batch(buf, lay, threshold_db=-30, min_silence_sec=0.4).cpu().numpy()
+    assert got2.tolist() == [orc.find_endpoint(w, -30, 0.4) for w in wavs]
+    assert ap.find_endpoint(torch.from_numpy(wavs[0]).cuda()) == want[0]
+    # trimmed conversion: the endpoints as length override
+    ends = ap.find_endpoint_batch(buf, lay)
+    pcm, off = ap.pcm16_batch(buf, lay, lens=ends)
+    off = off.cpu().numpy()
+    for u, w in enumerate(wavs):
+        assert np.array_equal(pcm[off[u]:off[u + 1]].cpu().numpy(), orc.save_wav_int16(w[:want[u]].astype(np.float64)))
+
+
+def test_save_wav_from_device_and_server_sentences(golden, tmp_path):
+    """save_wav of a CUDA waveform writes the bytes scipy writes for the oracle's int16 samples; the server's
+    sentence loop (server/synthesizer.py:133-162) as one batch."""
+    import io
+    from scipy.io import wavfile
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=8)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    w = synth_speech_like(77, n_samples=30000)
+    path = str(tmp_path / "dev.wav")
+    ap.save_wav(torch.from_numpy(w).cuda(), path)
+    ref = io.BytesIO()
+    wavfile.write(ref, audio["sample_rate"], orc.save_wav_int16(w.astype(np.float64)))
+    assert open(path, "rb").read() == ref.getvalue()
+    # three "sentences": normalised mel spectrograms as a Tacotron2 postnet would leave them on the device
+    mels = [orc.melspectrogram(synth_speech_like(80 + i, n_samples=275 * n)).astype(np.float32) for i, n in enumerate((40, 75, 23))]
+    angs = [(2 * np.pi * np.random.default_rng(i).random((1025, m.shape[1]))).astype(np.float32) for i, m in enumerate(mels)]
+    ang_packed = torch.from_numpy(np.ascontiguousarray(np.concatenate([a.T for a in angs]))).cuda()
+    data = ap.sentences_to_wav_bytes([torch.from_numpy(np.ascontiguousarray(m.T)).cuda() for m in mels], init_angles=ang_packed)
+    sr, pcm = wavfile.read(io.BytesIO(data))
+    assert sr == audio["sample_rate"] and pcm.dtype == np.int16
+    wavs_o = [orc.inv_mel_spectrogram(m, init_angles=a) for m, a in zip(mels, angs)]
+    want = orc.save_wav_int16(orc.server_concat(wavs_o))
+    assert len(pcm) == len(want) == sum(len(x) + 10000 for x in wavs_o)
+    assert np.abs(pcm.astype(int) - want.astype(int)).max() <= 2             # float32 Griffin-Lim vs float64: +-1 LSB
+    assert snr_db(want.astype(np.float64), pcm.astype(np.float64)) >= 55.0

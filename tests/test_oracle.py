@@ -142,3 +142,27 @@ def test_gl_sc_log_and_fp32_headroom():
     assert y.shape == (275 * (spec.shape[1] - 1),)
     assert sc.shape == (12,) and sc[-1] < sc[0]
     assert np.all(np.isfinite(y))
+
+
+def test_save_wav_int16_matches_reference_formula_and_scipy_container(tmp_path):
+    """Oracle save_wav_int16 == the reference expression (utils/audio.py:57) for a float64 waveform; the product's
+    RIFF writer is byte-identical to scipy.io.wavfile.write (utils/audio.py:58)."""
+    import io
+    from scipy.io import wavfile
+    from your_voice_tts_b200 import AudioProcessor
+    orc = OracleAudioProcessor(**MAIN_AUDIO)
+    rng = np.random.default_rng(3)
+    for scale in (1.0, 0.003, 40.0):
+        wav = rng.standard_normal(5000) * scale
+        ref = (wav * (32767 / max(0.01, np.max(np.abs(wav))))).astype(np.int16)
+        np.testing.assert_array_equal(orc.save_wav_int16(wav), ref)
+    w32 = (rng.standard_normal(5000) * 0.2).astype(np.float32)
+    got = orc.save_wav_int16(w32)
+    assert np.abs(got.astype(int) - orc.save_wav_int16(w32.astype(np.float64)).astype(int)).max() <= 1
+    cat = orc.server_concat([[0.5, -0.25], [1.0]], gap=3)
+    np.testing.assert_array_equal(cat, [0.5, -0.25, 0, 0, 0, 1.0, 0, 0, 0])
+    ap = AudioProcessor(verbose=False, **MAIN_AUDIO)
+    pcm = rng.integers(-32768, 32767, size=4321).astype(np.int16)
+    ref = io.BytesIO()
+    wavfile.write(ref, MAIN_AUDIO["sample_rate"], pcm)
+    assert ap.wav_file_bytes(pcm) == ref.getvalue()

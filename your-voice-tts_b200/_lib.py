@@ -20,6 +20,7 @@ SPEC_MAGNITUDE, SPEC_NORM_DB = 0, 1
 GL_DEEMPHASIS = 1
 MEL_IN_AMPLITUDE, MEL_IN_NORM_DB = 0, 1
 MEL_OUT_PLAIN, MEL_OUT_POWER, MEL_OUT_NORM_DB = 0, 1, 2
+PCM_JOINT_PEAK, PCM_F32_ARITH = 1, 2
 PW_NORMALIZE, PW_DENORMALIZE, PW_AMP_TO_DB, PW_DB_TO_AMP = 0, 1, 2, 3
 
 
@@ -59,6 +60,11 @@ PROTOTYPES = {
     "ttsa_preemphasis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ttsa_deemphasis_workspace_bytes": (c_size_t, [c_void_p, c_void_p]),
     "ttsa_deemphasis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ttsa_wav_peaks": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ttsa_find_endpoint": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p]),
+    "ttsa_pcm16_workspace_bytes": (c_size_t, [c_void_p, c_void_p]),
+    "ttsa_wav_to_pcm16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_int64, c_void_p, c_void_p, c_int64,
+                                  c_void_p, c_size_t, c_void_p]),
     "ttsa_pointwise": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "ttsa_transpose": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
 }

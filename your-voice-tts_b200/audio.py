@@ -260,7 +260,8 @@ class AudioProcessor(object):
         if not t.is_cuda or not t.is_contiguous():
             raise ValueError("expected a contiguous CUDA tensor, got %s strides %s on %s"
                              % (tuple(t.shape), tuple(t.stride()), t.device))
-        if t.dtype not in (_torch().float32, _torch().uint8):
+        torch = _torch()
+        if t.dtype not in (torch.float32, torch.uint8, torch.int16, torch.int32, torch.int64):
             raise ValueError("expected a float32 tensor, got %s" % t.dtype)
         return ctypes.c_void_p(t.data_ptr())
 
@@ -424,8 +425,87 @@ class AudioProcessor(object):
         return lay.split_wav(out)
 
     # ------------------------------------------------------------------------------------------ reference API
+    # ------------------------------------------------------------------------------------------ waveform post-processing
+    def wav_peaks_batch(self, wav_packed, layout, lens=None):
+        """max |wav_u| per utterance: the peak save_wav normalises by (utils/audio.py:57).  -> [B] float32"""
+        torch = _torch()
+        plan = layout.plan
+        out = torch.empty((max(1, layout.n_utts),), dtype=torch.float32, device=wav_packed.device)
+        L.check(plan.lib.ttsa_wav_peaks(plan.handle, layout.handle, self._ptr(wav_packed), self._ptr(lens),
+                                        self._ptr(out), self._stream()))
+        return out[:layout.n_utts]
+
+    def find_endpoint_batch(self, wav_packed, layout, threshold_db=-40, min_silence_sec=0.8):
+        """find_endpoint of every utterance (utils/audio.py:203-210).  -> [B] int32 on the device"""
+        torch = _torch()
+        plan = layout.plan
+        out = torch.empty((max(1, layout.n_utts),), dtype=torch.int32, device=wav_packed.device)
+        L.check(plan.lib.ttsa_find_endpoint(plan.handle, layout.handle, self._ptr(wav_packed), float(threshold_db),
+                                            float(min_silence_sec), self._ptr(out), self._stream()))
+        return out[:layout.n_utts]
+
+    def pcm16_batch(self, wav_packed, layout, lens=None, joint_peak=False, gap_samples=0, float32_arith=False):
+        """save_wav's int16 conversion for a packed batch (utils/audio.py:56-58), optionally trimmed to `lens`
+        (device int32 [B], e.g. find_endpoint_batch) and laid out as the server concatenates sentences:
+        every utterance followed by `gap_samples` zeros, ONE peak for the whole output (joint_peak;
+        server/synthesizer.py:157-161).  -> (int16 tensor [capacity], offsets int64 [B+1] on the device;
+        offsets[B] = samples written)."""
+        torch = _torch()
+        plan = layout.plan
+        dev = wav_packed.device
+        B = layout.n_utts
+        cap = int(np.sum(layout.wav_len)) + int(gap_samples) * B
+        out = torch.zeros((max(1, cap),), dtype=torch.int16, device=dev)
+        off = torch.zeros((B + 1,), dtype=torch.int64, device=dev)
+        ws = torch.empty((int(plan.lib.ttsa_pcm16_workspace_bytes(plan.handle, layout.handle)),), dtype=torch.uint8, device=dev)
+        flags = (L.PCM_JOINT_PEAK if joint_peak else 0) | (L.PCM_F32_ARITH if float32_arith else 0)
+        L.check(plan.lib.ttsa_wav_to_pcm16(plan.handle, layout.handle, self._ptr(wav_packed), self._ptr(lens), flags,
+                                           int(gap_samples), self._ptr(off), self._ptr(out), cap, self._ptr(ws),
+                                           ws.numel(), self._stream()))
+        return out, off
+
+    def wav_file_bytes(self, pcm16):
+        """RIFF/WAVE container around mono int16 samples at self.sample_rate -- byte-identical to what
+        scipy.io.wavfile.write(path, sample_rate, int16_array) puts in the file (utils/audio.py:58)."""
+        import struct
+        data = np.ascontiguousarray(np.asarray(pcm16, dtype="<i2")).tobytes()
+        sr = int(self.sample_rate)
+        hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE"
+        hdr += b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, sr, sr * 2, 2, 16)
+        hdr += b"data" + struct.pack("<I", len(data))
+        return hdr + data
+
+    def sentences_to_wav_bytes(self, mels, init_angles=None, seed=0, gap_samples=10000):
+        """The audio half of Synthesizer.tts (server/synthesizer.py:133-162) for a Tacotron2 model without WaveRNN:
+        every sentence's postnet output [T_i, num_mels] (CUDA tensors, as the model leaves them) goes through ONE
+        batched inv_mel_spectrogram instead of a per-sentence CPU loop, `gap_samples` zeros follow each sentence, and
+        the concatenation is peak-normalised to int16 and wrapped as a WAV file.  Returns bytes."""
+        torch = _torch()
+        dev = self._dev()
+        Ts = [int(m.shape[0]) for m in mels]
+        lay = self.layout(n_frames=Ts)
+        packed = torch.cat([self._to_dev(m) for m in mels], dim=0).contiguous()
+        wav = self.inv_mel_spectrogram_batch(packed, lay, init_angles=init_angles, seed=seed)
+        pcm, off = self.pcm16_batch(wav, lay, joint_peak=True, gap_samples=gap_samples)
+        n = int(off[-1].item())
+        return self.wav_file_bytes(pcm[:n].cpu().numpy())
+
     def save_wav(self, wav, path):
-        """utils/audio.py:56-58"""
+        """utils/audio.py:56-58.  A CUDA waveform is normalised and converted on the device and only the int16
+        samples cross to the host; arrays and lists take the reference's own numpy/scipy route."""
+        if self._is_tensor(wav) and wav.is_cuda:
+            t = wav.reshape(-1).to(_torch().float32).contiguous()
+            lay = self.layout(wav_lengths=[int(t.numel())])
+            buf = _torch().zeros((max(1, lay.total_samples),), dtype=_torch().float32, device=t.device)
+            buf[:t.numel()].copy_(t)
+            pcm, off = self.pcm16_batch(buf, lay)
+            data = self.wav_file_bytes(pcm[:t.numel()].cpu().numpy())
+            if hasattr(path, "write"):
+                path.write(data)
+            else:
+                with open(path, "wb") as f:
+                    f.write(data)
+            return
         from scipy.io import wavfile
         wav = np.asarray(wav)
         wav_norm = wav * (32767 / max(0.01, np.max(np.abs(wav))))
@@ -599,6 +679,12 @@ class AudioProcessor(object):
     # (file I/O and O(L) scalar post-processing: outside the kernel scope, kept for drop-in completeness)
     def find_endpoint(self, wav, threshold_db=-40, min_silence_sec=0.8):
         """utils/audio.py:203-210"""
+        if self._is_tensor(wav) and wav.is_cuda:
+            t = wav.reshape(-1).to(_torch().float32).contiguous()
+            lay = self.layout(wav_lengths=[int(t.numel())])
+            buf = _torch().zeros((max(1, lay.total_samples),), dtype=_torch().float32, device=t.device)
+            buf[:t.numel()].copy_(t)
+            return int(self.find_endpoint_batch(buf, lay, threshold_db, min_silence_sec)[0].item())
         window_length = int(self.sample_rate * min_silence_sec)
         hop_length = int(window_length / 4)
         threshold = np.power(10.0, threshold_db * 0.05)

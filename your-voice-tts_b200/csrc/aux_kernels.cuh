@@ -75,6 +75,103 @@ __global__ void preemphasis_kernel(BatchDev bd, float p, const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Waveform post-processing (the steps right after the synthesis path)
+//   save_wav scaling      wav * (32767 / max(0.01, max|wav|)) -> int16      (utils/audio.py:56-58)
+//   find_endpoint         first silent window                                (utils/audio.py:203-210)
+//   sentence gaps         10 000 zero samples after every sentence           (server/synthesizer.py:157-161)
+// Packed waveforms; an optional per-utterance length override (e.g. the endpoints) replaces BatchDev::wav_len.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int wav_len_of(const BatchDev& bd, const int* lens, int u) {
+  const int L = bd.wav_len[u];
+  if (lens == nullptr) return L;
+  const int v = lens[u];
+  return v < 0 ? 0 : (v < L ? v : L);
+}
+
+// peaks[u] = max |wav_u|  (bit pattern of a non-negative float orders like an unsigned integer); peaks zeroed by the caller
+__global__ void wav_peak_kernel(BatchDev bd, const int* __restrict__ lens, const float* __restrict__ wav, unsigned* __restrict__ peaks) {
+  const int u = blockIdx.y;
+  const int L = wav_len_of(bd, lens, u);
+  const float* x = wav + bd.wav_off[u];
+  float m = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(peaks + u, __float_as_uint(m));
+}
+
+// endpoints[u] = first x + hop with max(wav[x : x + window]) < threshold, x = hop, 2 hop, ... < L - window; else L.
+// One CTA per (candidate, utterance); endpoints pre-set to L by wav_endpoint_init_kernel.
+__global__ void wav_endpoint_init_kernel(BatchDev bd, int* __restrict__ endpoints) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < bd.B) endpoints[u] = bd.wav_len[u];
+}
+__global__ void wav_endpoint_kernel(BatchDev bd, const float* __restrict__ wav, int window, int hop, double threshold,
+                                    int* __restrict__ endpoints) {
+  const int u = blockIdx.y;
+  const int L = bd.wav_len[u];
+  const int x0 = (blockIdx.x + 1) * hop;
+  if (x0 >= L - window) return;
+  const float* x = wav + bd.wav_off[u] + x0;
+  float m = -INFINITY;                                     // the reference takes the SIGNED maximum, not max |x|
+  for (int i = threadIdx.x; i < window; i += blockDim.x) m = fmaxf(m, x[i]);
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    if ((double)m < threshold) atomicMin(endpoints + u, x0 + hop);
+  }
+}
+
+// out_off[u] = sum_{v<u} (len_v + gap), out_off[B] = total; peaks -> per-utterance (or joint) scale
+// 32767 / max(0.01, peak) in float64.  One CTA.
+__global__ void pcm_plan_kernel(BatchDev bd, const int* __restrict__ lens, const unsigned* __restrict__ peaks, int joint,
+                                long long gap, long long* __restrict__ out_off, double* __restrict__ scales) {
+  __shared__ float s_peak;
+  if (threadIdx.x == 0) {
+    long long acc = 0;
+    float pk = 0.0f;
+    for (int u = 0; u < bd.B; ++u) {
+      out_off[u] = acc;
+      acc += wav_len_of(bd, lens, u) + gap;
+      pk = fmaxf(pk, __uint_as_float(peaks[u]));
+    }
+    out_off[bd.B] = acc;
+    s_peak = pk;
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < bd.B; u += blockDim.x) {
+    const double pk = (double)(joint ? s_peak : __uint_as_float(peaks[u]));
+    scales[u] = 32767.0 / fmax(0.01, pk);
+  }
+}
+
+// int16 conversion: numpy astype(np.int16) of the scaled sample = truncation toward zero.  f32_arith: the product is
+// formed in float32 with the float64 scale rounded to float32 (what the reference computes for a float32 waveform
+// under its pinned numpy); otherwise in float64 (float64 waveform: the reference's default path, de-emphasis and the
+// server's list concatenation both widen).
+__global__ void pcm_convert_kernel(BatchDev bd, const int* __restrict__ lens, const float* __restrict__ wav,
+                                   const long long* __restrict__ out_off, const double* __restrict__ scales, long long gap,
+                                   int f32_arith, long long capacity, short* __restrict__ out) {
+  const int u = blockIdx.y;
+  const int L = wav_len_of(bd, lens, u);
+  const float* x = wav + bd.wav_off[u];
+  const long long o0 = out_off[u];
+  const double sc = scales[u];
+  const float scf = (float)sc;
+  const long long n = L + gap;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (o0 + i >= capacity) break;
+    short v = 0;
+    if (i < L) v = f32_arith ? (short)(int)__fmul_rn(x[i], scf) : (short)(int)((double)x[i] * sc);
+    out[o0 + i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // apply_inv_preemphasis: y[n] = x[n] + p y[n-1]   (utils/audio.py:133-136)
 // first-order linear recurrence as a blocked scan: chunks of kDeChunk samples, one CTA each.
 //   pass 1: zero-state response of every chunk at its last sample (chunk aggregate)

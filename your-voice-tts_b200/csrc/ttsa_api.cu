@@ -590,6 +590,91 @@ extern "C" int ttsa_deemphasis(const ttsa_plan* plan, const ttsa_batch* batch, c
   return deemph_launch(plan, batch, x_dev, y_dev, (float*)workspace_dev, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// waveform post-processing
+// ---------------------------------------------------------------------------------------------------------
+static dim3 wav_grid(const ttsa_batch* batch, long long extra = 0) {
+  long long maxlen = 0;
+  for (int v : batch->wav_len) maxlen = std::max<long long>(maxlen, v);
+  maxlen += extra;
+  return dim3((unsigned)std::max<long long>(1, std::min<long long>(1024, (maxlen + 1023) / 1024)), (unsigned)batch->B);
+}
+
+extern "C" int ttsa_wav_peaks(const ttsa_plan* plan, const ttsa_batch* batch, const float* wav_dev, const int32_t* lens_dev,
+                              float* peaks_dev, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!wav_dev || !peaks_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  if (batch->B == 0) return TTSA_OK;
+  DeviceGuard guard(plan->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(peaks_dev, 0, (size_t)batch->B * 4, st));
+  wav_peak_kernel<<<wav_grid(batch), 256, 0, st>>>(batch->dev, lens_dev, wav_dev, (unsigned*)peaks_dev);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
+extern "C" int ttsa_find_endpoint(const ttsa_plan* plan, const ttsa_batch* batch, const float* wav_dev, double threshold_db,
+                                  double min_silence_sec, int32_t* endpoints_dev, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!wav_dev || !endpoints_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  const int window = (int)(plan->cfg.sample_rate * min_silence_sec);
+  const int hop = window / 4;
+  if (window < 4) return fail(TTSA_ERR_BAD_ARG, "min_silence_sec %g gives a window of %d samples", min_silence_sec, window);
+  if (batch->B == 0) return TTSA_OK;
+  DeviceGuard guard(plan->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  wav_endpoint_init_kernel<<<(batch->B + 255) / 256, 256, 0, st>>>(batch->dev, endpoints_dev);
+  g_launches += 1;
+  long long maxlen = 0;
+  for (int v : batch->wav_len) maxlen = std::max<long long>(maxlen, v);
+  // candidates x = hop, 2 hop, ... < L - window
+  const long long ncand = maxlen - window > hop ? (maxlen - window - hop + hop - 1) / hop : 0;
+  if (ncand > 0) {
+    const double threshold = std::pow(10.0, threshold_db * 0.05);          // _db_to_amp, utils/audio.py:125-126
+    wav_endpoint_kernel<<<dim3((unsigned)ncand, (unsigned)batch->B), 256, 0, st>>>(batch->dev, wav_dev, window, hop, threshold,
+                                                                                  endpoints_dev);
+    g_launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
+extern "C" size_t ttsa_pcm16_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* batch) {
+  if (!plan || !batch) return 0;
+  return ((size_t)batch->B * 8 + 255) / 256 * 256 + ((size_t)batch->B * 4 + 255) / 256 * 256 + 256;
+}
+
+extern "C" int ttsa_wav_to_pcm16(const ttsa_plan* plan, const ttsa_batch* batch, const float* wav_dev, const int32_t* lens_dev,
+                                 uint32_t flags, int64_t gap_samples, int64_t* out_off_dev, int16_t* out_dev,
+                                 int64_t out_capacity, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (int rc = check_work(plan, batch)) return rc;
+  if (!wav_dev || !out_off_dev || !out_dev || !workspace_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
+  if (gap_samples < 0 || out_capacity < 0) return fail(TTSA_ERR_BAD_ARG, "negative gap or capacity");
+  if (workspace_bytes < ttsa_pcm16_workspace_bytes(plan, batch)) return fail(TTSA_ERR_WORKSPACE, "workspace too small");
+  long long sum_len = 0;
+  for (int v : batch->wav_len) sum_len += v;
+  if (lens_dev == nullptr && out_capacity < sum_len + gap_samples * batch->B)
+    return fail(TTSA_ERR_BAD_ARG, "out_capacity %lld < %lld samples", (long long)out_capacity,
+                (long long)(sum_len + gap_samples * batch->B));
+  if (batch->B == 0) return TTSA_OK;
+  DeviceGuard guard(plan->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* scales = (double*)workspace_dev;
+  unsigned* peaks = (unsigned*)((char*)workspace_dev + ((size_t)batch->B * 8 + 255) / 256 * 256);
+  CUDA_TRY(cudaMemsetAsync(peaks, 0, (size_t)batch->B * 4, st));
+  wav_peak_kernel<<<wav_grid(batch), 256, 0, st>>>(batch->dev, lens_dev, wav_dev, peaks);
+  pcm_plan_kernel<<<1, 256, 0, st>>>(batch->dev, lens_dev, peaks, (flags & TTSA_PCM_JOINT_PEAK) ? 1 : 0, (long long)gap_samples,
+                                     (long long*)out_off_dev, scales);
+  pcm_convert_kernel<<<wav_grid(batch, gap_samples), 256, 0, st>>>(batch->dev, lens_dev, wav_dev, (const long long*)out_off_dev,
+                                                                  scales, (long long)gap_samples,
+                                                                  (flags & TTSA_PCM_F32_ARITH) ? 1 : 0, (long long)out_capacity,
+                                                                  (short*)out_dev);
+  g_launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
 extern "C" int ttsa_preemphasis(const ttsa_plan* plan, const ttsa_batch* batch, const float* x_dev, float* y_dev, void* stream) {
   if (int rc = check_work(plan, batch)) return rc;
   if (!x_dev || !y_dev || x_dev == y_dev) return fail(TTSA_ERR_BAD_ARG, "null or aliasing buffers");
