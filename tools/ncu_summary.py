@@ -1,0 +1,25 @@
+"""Summarise an ncu report (raw page) into the JSON kept under profiles/.
+usage: ncu_summary.py <report.ncu-rep> <out.json> "<note>" """
+import csv, json, subprocess, sys, io
+rep, out, note = sys.argv[1], sys.argv[2], sys.argv[3]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, data = rows[0], rows[1], rows[2:]
+want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max"]
+want += [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
+launches = []
+for d in data:
+    e = {}
+    for w in want:
+        if w in hdr:
+            i = hdr.index(w)
+            e[w + (" [%s]" % units[i] if units[i] else "")] = d[i]
+    launches.append(e)
+json.dump({"note": note, "launches": launches}, open(out, "w"), indent=1)
+for e in launches:
+    print(e["Kernel Name"][:60], e.get("gpu__time_duration.sum [us]"))
