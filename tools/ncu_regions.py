@@ -6,7 +6,7 @@ def find(s):
     return next(i+1 for i,l in enumerate(lines) if s in l)
 marks=[('setup',0),('stage helpers',find('span staging helpers')),('tile loop/stage',find('previous segment is done with planes')),('frame load',find('window the frame')),
        ('middle',find('per-bin step -> conj')),('shfl2',find('hand the partner its half')),('transform glue',find('1024-point transform, 32 x 32')),('analysis out',find('spectrum out')),
-       ('slot store',find("the warp's overlap-add slot")),('post-frame sync/stage_load',find('next span: its loads are issued by each warp')),('OLA',find('overlap-add + window + 1/(N wss) + store')),('stage_store/sync',find('stage_store(jt + 1);')),('sc',find('if constexpr (MODE == MODE_GL_ITER && SC)'))]
+       ('slot store',find("the warp's overlap-add slot")),('post-frame sync/stage_load',find('next span: its loads are issued by each warp')),('OLA',find('overlap-add + window + 1/(N wss) + store')),('stage_store/sync',find('if (have_next && !(a.debug & 2)) stage_store(')),('sc',find('if constexpr (MODE == MODE_GL_ITER && SC)'))]
 helper_end=find('// the kernel')
 def region(l):
     if l is None: return 'none'
