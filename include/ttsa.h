@@ -25,9 +25,10 @@
  *     (multiple of 4 samples) and holds wav_len[u] samples.
  *   - Every function returns 0 on success or a negative ttsa_status; ttsa_last_error()
  *     gives a thread-local message.  No exception crosses the ABI.
- *   - v1 supports num_freq == 1025 (n_fft == 2048), the value of every shipped config
- *     (config*.json:"num_freq"), hop <= win <= 9*hop, win <= 2048.  Anything else ->
- *     TTSA_ERR_UNSUPPORTED.  There is no CPU fallback anywhere in this library.
+ *   - num_freq == 1025 (n_fft == 2048), the value of every shipped config (config*.json:"num_freq"), runs the tuned
+ *     warp-per-frame kernels (hop <= win <= 9*hop, win <= 2048).  Any other power-of-two n_fft in [256, 4096]
+ *     (num_freq 129 ... 2049, hop <= win <= n_fft) runs an untuned one-CTA-per-frame path with the same semantics.
+ *     Anything else -> TTSA_ERR_UNSUPPORTED.  There is no CPU fallback anywhere in this library.
  */
 #ifndef TTSA_H_
 #define TTSA_H_

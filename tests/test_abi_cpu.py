@@ -44,6 +44,21 @@ def test_mel_basis_and_pinv_match_oracle(audio):
     np.testing.assert_allclose(P, Pref, atol=1e-10 * np.abs(Pref).max())
 
 
+def test_other_transform_sizes_host_tables():
+    """num_freq 257 / 513 / 2049 (n_fft 512 / 1024 / 4096) are served by the any-size path: plan creation succeeds
+    and the mel basis / pseudo-inverse follow the oracle for that n_fft."""
+    for nf, flm, fsm in ((257, 20.0, 5.0), (513, 40.0, 10.0), (2049, 50.0, 12.5)):
+        audio = dict(MAIN_AUDIO, num_freq=nf, frame_length_ms=flm, frame_shift_ms=fsm)
+        ap = AudioProcessor(verbose=False, **audio)
+        orc = OracleAudioProcessor(**audio)
+        assert ap.n_fft == (nf - 1) * 2 and ap.win_length <= ap.n_fft
+        M = ap._build_mel_basis()
+        assert M.shape == (80, nf)
+        np.testing.assert_allclose(M, orc._build_mel_basis(), atol=1e-14)
+        Pref = np.linalg.pinv(orc._build_mel_basis())
+        np.testing.assert_allclose(ap._inv_mel_basis(), Pref, atol=1e-9 * np.abs(Pref).max())
+
+
 def test_mel_basis_matches_reference_shim_golden(golden):
     ap = AudioProcessor(verbose=False, **MAIN_AUDIO)
     np.testing.assert_allclose(ap._build_mel_basis(), golden["main_mel_basis"], atol=2e-7)
@@ -84,6 +99,12 @@ def test_error_codes_and_messages():
     assert rc == L.TTSA_ERR_NO_DEVICE
     # config validation
     with pytest.raises(L.TtsaError) as ei:
+        AudioProcessor(verbose=False, **dict(MAIN_AUDIO, num_freq=1001))._plan(host_only=True)   # n_fft 2000: not a power of two
+    assert ei.value.code == L.TTSA_ERR_UNSUPPORTED
+    with pytest.raises(L.TtsaError) as ei:
+        AudioProcessor(verbose=False, **dict(MAIN_AUDIO, num_freq=4097))._plan(host_only=True)   # n_fft 8192 > 4096
+    assert ei.value.code == L.TTSA_ERR_UNSUPPORTED
+    with pytest.raises(L.TtsaError) as ei:                                                        # win 1102 > n_fft 1024
         AudioProcessor(verbose=False, **dict(MAIN_AUDIO, num_freq=513))._plan(host_only=True)
     assert ei.value.code == L.TTSA_ERR_UNSUPPORTED
     with pytest.raises(AssertionError):     # utils/audio.py:70-71

@@ -503,3 +503,41 @@ def test_save_wav_from_device_and_server_sentences(golden, tmp_path):
     assert len(pcm) == len(want) == sum(len(x) + 10000 for x in wavs_o)
     assert np.abs(pcm.astype(int) - want.astype(int)).max() <= 2             # float32 Griffin-Lim vs float64: +-1 LSB
     assert snr_db(want.astype(np.float64), pcm.astype(np.float64)) >= 55.0
+
+
+# ------------------------------------------------------------------------------------------------ other transform sizes
+@pytest.mark.parametrize("nf_flm_fsm", [(257, 20.0, 5.0), (513, 40.0, 10.0), (513, 46.4, 11.6), (2049, 50.0, 12.5), (2049, 185.0, 30.0)])
+def test_other_num_freq_any_size_path(nf_flm_fsm):
+    """num_freq != 1025 (n_fft 512 / 1024 / 4096) runs the any-size kernels: same bars as the main path -- forward
+    1e-4, stft/istft vs the oracle, Griffin-Lim >= 60 dB with injected phases, spectral convergence per iteration."""
+    nf, flm, fsm = nf_flm_fsm
+    audio = dict(MAIN_AUDIO, num_freq=nf, frame_length_ms=flm, frame_shift_ms=fsm, griffin_lim_iters=6)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    hop = orc.hop_length
+    y = synth_speech_like(21, n_samples=hop * 57 + 13)
+    spec, spec_o = ap.spectrogram(y), orc.spectrogram(y)
+    mel, mel_o = ap.melspectrogram(y), orc.melspectrogram(y)
+    assert spec.shape == spec_o.shape == (nf, 58) and mel.shape == mel_o.shape
+    assert np.mean(np.abs(spec - spec_o) <= FWD_TOL) >= 0.995
+    assert np.mean(np.abs(mel - mel_o) <= FWD_TOL) >= 0.995
+    D, Do = ap._stft(y), lr_stft(y.astype(np.float64), orc.n_fft, orc.hop_length, orc.win_length)
+    assert np.abs(D - Do).max() <= 2e-6 * np.abs(Do).max()
+    yi, yio = ap._istft(Do.astype(np.complex64)), lr_istft(Do.astype(np.complex64).astype(np.complex128), orc.hop_length, orc.win_length)
+    assert snr_db(yio, yi) >= 100.0
+    ang = (2 * np.pi * np.random.default_rng(2).random(spec_o.shape)).astype(np.float32)
+    w, sc = ap.inv_spectrogram(spec_o.astype(np.float32), init_angles=ang, return_sc=True)
+    wo, sco = orc.inv_spectrogram(spec_o.astype(np.float32), init_angles=ang, return_sc=True)
+    assert w.shape == wo.shape and snr_db(wo, w) >= GL_SNR_DB, snr_db(wo, w)
+    np.testing.assert_allclose(sc, sco, rtol=SC_RTOL)
+    wm = ap.inv_mel_spectrogram(mel_o.astype(np.float32), init_angles=ang)
+    wmo = orc.inv_mel_spectrogram(mel_o.astype(np.float32), init_angles=ang)
+    assert snr_db(wmo, wm) >= GL_SNR_DB, snr_db(wmo, wm)
+    lm, lmo = ap.out_linear_to_mel(spec_o.astype(np.float32)), orc.out_linear_to_mel(spec_o.astype(np.float32))
+    assert np.mean(np.abs(lm - lmo) <= FWD_TOL) >= 0.995
+    # ragged batch, device RNG, de-emphasis
+    Ts = [17, 1, 40, 3]
+    lay = ap.layout(n_frames=Ts)
+    specs = torch.rand((sum(Ts), nf), device="cuda")
+    out = ap.inv_spectrogram_batch(specs, lay, seed=3)
+    assert all(torch.isfinite(o).all() for o in lay.split_wav(out))
+    assert [int(o.numel()) for o in lay.split_wav(out)] == [hop * max(0, t - 1) for t in Ts]

@@ -276,6 +276,7 @@ struct MelParams {
   float n_a, n_b, n_lo, n_hi, min_amp;
   float power;
   int num_mels;
+  int F;                 // bins per row (num_freq)
   long long rows;
 };
 
@@ -336,7 +337,7 @@ mel_to_linear_kernel(MelParams p, const float* __restrict__ pinvT /*[K][ldp]*/, 
   const long long row0 = (long long)blockIdx.y * kMtlRows;
   for (int i = threadIdx.x; i < K * kMtlBins; i += 256) {
     const int m = i / kMtlBins, b = i % kMtlBins;
-    Ps[i] = (bin0 + b) < kF ? pinvT[(long long)m * ldp + bin0 + b] : 0.0f;
+    Ps[i] = (bin0 + b) < p.F ? pinvT[(long long)m * ldp + bin0 + b] : 0.0f;
   }
   for (int i = threadIdx.x; i < K * kMtlRows; i += 256) {
     const int r = i / K, m = i % K;        // coalesced over m
@@ -369,10 +370,10 @@ mel_to_linear_kernel(MelParams p, const float* __restrict__ pinvT /*[K][ldp]*/, 
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int k = bin0 + tb_ * 4 + b;
-      if (k < kF) {
+      if (k < p.F) {
         float v = fmaxf(1e-10f, acc[r][b]);
         if (out_kind == 1) v = powf(v, p.power);
-        lin[row * kF + k] = v;
+        lin[row * p.F + k] = v;
       }
     }
   }

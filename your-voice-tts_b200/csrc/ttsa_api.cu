@@ -11,6 +11,7 @@
 
 #include "../../include/ttsa.h"
 #include "aux_kernels.cuh"
+#include "generic_kernels.cuh"
 #include "frame_launch.cuh"
 #include "host_tables.hpp"
 #include "mel_gemm_tc.cuh"
@@ -63,6 +64,9 @@ struct ttsa_plan {
   std::vector<double> h_inv_mel;   // [F][num_mels]
   int nz = 32;                     // compile-time zero-pruning class of the frame kernels (20 or 32)
   int ctas_per_sm = 1;
+  bool generic = false;            // n_fft != 2048: the any-size kernels of generic_kernels.cuh
+  GenGeo gg;
+  GenTables gt;
   bool fixed_geo = true;           // use the kernels compiled for this (hop, win) when they exist (TTSA_GENERIC_GEO=1: never)
   // device allocations
   void* d_block = nullptr;         // one allocation holding every table
@@ -182,6 +186,98 @@ static std::vector<uint16_t> canon_split_b(const std::vector<double>& B, int n_r
   return out;
 }
 
+// Tables of the any-size path (generic_kernels.cuh): twiddles, window, banded mel basis, transposed pseudo-inverse.
+static int plan_create_generic(ttsa_plan* p, int logn) {
+  const ttsa_config& c = p->cfg;
+  const int N = c.n_fft, F = c.num_freq;
+  GenGeo& g = p->gg;
+  g.n_fft = N; g.logn = logn; g.F = F; g.hop = c.hop_length; g.win = c.win_length;
+  g.lpad = (N - c.win_length) / 2; g.off0 = N / 2 - g.lpad; g.num_mels = c.num_mels;
+  g.preemph = (float)c.preemphasis;
+  g.s_c1 = p->geo.s_c1; g.s_c0 = p->geo.s_c0; g.s_lo = p->geo.s_lo; g.s_hi = p->geo.s_hi;
+  g.n_a = p->geo.n_a; g.n_b = p->geo.n_b; g.n_lo = p->geo.n_lo; g.n_hi = p->geo.n_hi; g.min_amp = p->geo.min_amp;
+  std::vector<float> h_tw((size_t)N), h_win(c.win_length);
+  for (int k = 0; k < N / 2; ++k) {
+    const double ang = 2.0 * ttsa_host::kPi * k / N;
+    h_tw[2 * k] = (float)std::cos(ang);
+    h_tw[2 * k + 1] = (float)-std::sin(ang);
+  }
+  const std::vector<double> w = ttsa_host::hann_periodic(c.win_length);
+  for (int m = 0; m < c.win_length; ++m) h_win[m] = (float)w[m];
+  std::vector<int> h_lo(c.num_mels, 0), h_cnt(c.num_mels, 0);
+  int ld = 1;
+  for (int m = 0; m < c.num_mels; ++m) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < F; ++k)
+      if (p->h_mel[(size_t)m * F + k] != 0.0) { if (lo < 0) lo = k; hi = k; }
+    if (lo >= 0) { h_lo[m] = lo; h_cnt[m] = hi - lo + 1; ld = std::max(ld, hi - lo + 1); }
+  }
+  ld = round_up(ld, 4);
+  std::vector<float> h_val((size_t)c.num_mels * ld, 0.f);
+  for (int m = 0; m < c.num_mels; ++m)
+    for (int cidx = 0; cidx < h_cnt[m]; ++cidx) h_val[(size_t)m * ld + cidx] = (float)p->h_mel[(size_t)m * F + h_lo[m] + cidx];
+  p->ldp = round_up(F, 4);
+  std::vector<float> h_pinvT((size_t)c.num_mels * p->ldp, 0.f);
+  for (int k = 0; k < F; ++k)
+    for (int m = 0; m < c.num_mels; ++m) h_pinvT[(size_t)m * p->ldp + k] = (float)p->h_inv_mel[(size_t)k * c.num_mels + m];
+  struct Piece { const void* src; size_t bytes; size_t off; };
+  std::vector<Piece> pieces = {{h_tw.data(), h_tw.size() * 4, 0}, {h_win.data(), h_win.size() * 4, 0}, {h_lo.data(), h_lo.size() * 4, 0},
+                               {h_cnt.data(), h_cnt.size() * 4, 0}, {h_val.data(), h_val.size() * 4, 0},
+                               {h_pinvT.data(), h_pinvT.size() * 4, 0}};
+  size_t total = 0;
+  for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
+  if (cudaMalloc(&p->d_block, total) != cudaSuccess) return fail(TTSA_ERR_CUDA, "cudaMalloc(%zu) for plan tables failed", total);
+  for (auto& pc : pieces) {
+    cudaError_t e = cudaMemcpy((char*)p->d_block + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(p->d_block); p->d_block = nullptr; return fail(TTSA_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
+  }
+  char* base = (char*)p->d_block;
+  p->gt.tw = (const float2*)(base + pieces[0].off);
+  p->gt.win = (const float*)(base + pieces[1].off);
+  p->gt.mel_lo = (const int*)(base + pieces[2].off);
+  p->gt.mel_cnt = (const int*)(base + pieces[3].off);
+  p->gt.mel_val = (const float*)(base + pieces[4].off);
+  p->gt.mel_ld = ld;
+  p->d_pinvT = (const float*)(base + pieces[5].off);
+  p->ctas_per_sm = 1;
+  cudaError_t e = cudaFuncSetAttribute(mel_to_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kMtlMaxK * (kMtlBins + kMtlRows) * 4);
+  if (e != cudaSuccess) { cudaFree(p->d_block); p->d_block = nullptr; return fail(TTSA_ERR_CUDA, "mel kernel configuration: %s", cudaGetErrorString(e)); }
+  return TTSA_OK;
+}
+
+// launch one any-size frame kernel
+static int gen_launch(const ttsa_plan* plan, const ttsa_batch* batch, int mode, int src, FrameArgs a, cudaStream_t st) {
+  if (batch->total_frames == 0) return TTSA_OK;
+  a.rows_total = batch->total_frames;
+  const int grid = (int)std::min<long long>(batch->total_frames, (long long)plan->num_sms * 8);
+  const size_t smem = (size_t)plan->gg.n_fft * 8 + (size_t)(plan->gg.F + 1) * 4;
+  const GenGeo& g = plan->gg; const GenTables& t = plan->gt; const BatchDev& bd = batch->dev;
+#define TTSA_GEN(M, S) gen_frame_kernel<M, S><<<grid, kGenThreads, smem, st>>>(g, t, bd, a)
+  if (mode == MODE_ANALYSIS) { if (src == OUT_COMPLEX) TTSA_GEN(MODE_ANALYSIS, OUT_COMPLEX); else TTSA_GEN(MODE_ANALYSIS, OUT_FEATURES); }
+  else if (mode == MODE_GL_ITER) { if (src == SRC_MAG) TTSA_GEN(MODE_GL_ITER, SRC_MAG); else TTSA_GEN(MODE_GL_ITER, SRC_NORM_DB); }
+  else { if (src == SRC_MAG) TTSA_GEN(MODE_SYNTH, SRC_MAG); else if (src == SRC_NORM_DB) TTSA_GEN(MODE_SYNTH, SRC_NORM_DB); else TTSA_GEN(MODE_SYNTH, SRC_COMPLEX); }
+#undef TTSA_GEN
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
+// zero the waveform, overlap-add every frame into it, divide by the window sum of squares
+static int gen_synthesise(const ttsa_plan* plan, const ttsa_batch* batch, int mode, int src, const FrameArgs& a, cudaStream_t st) {
+  if (batch->total_samples == 0) return TTSA_OK;
+  CUDA_TRY(cudaMemsetAsync(a.wav_out, 0, (size_t)batch->total_samples * 4, st));
+  if (int rc = gen_launch(plan, batch, mode, src, a, st)) return rc;
+  int maxlen = 0;
+  for (int v : batch->wav_len) maxlen = std::max(maxlen, v);
+  if (maxlen == 0) return TTSA_OK;
+  dim3 grid((unsigned)std::max(1, std::min(1024, (maxlen + 255) / 256)), (unsigned)batch->B);
+  gen_wss_kernel<<<grid, 256, 0, st>>>(plan->gg, plan->gt, batch->dev, a.wav_out);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return TTSA_OK;
+}
+
 extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** out) {
   if (!cfg || !out) return fail(TTSA_ERR_BAD_ARG, "null argument");
   *out = nullptr;
@@ -191,10 +287,14 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   if (c.n_fft != (c.num_freq - 1) * 2) return fail(TTSA_ERR_BAD_CONFIG, "n_fft must equal (num_freq - 1) * 2");
   if (c.mel_fmax > 0 && c.mel_fmax > c.sample_rate / 2)   // assert at utils/audio.py:70-71 (integer sr // 2)
     return fail(TTSA_ERR_BAD_CONFIG, "mel_fmax %.1f > sample_rate // 2 = %d", c.mel_fmax, c.sample_rate / 2);
-  if (c.n_fft != kNfft) return fail(TTSA_ERR_UNSUPPORTED, "num_freq %d: only num_freq 1025 (n_fft 2048) is built", c.num_freq);
-  if (c.hop_length < 2 || c.win_length < c.hop_length || c.win_length > kNfft)
+  const bool generic = c.n_fft != kNfft;
+  int logn = 0;
+  while ((1 << logn) < c.n_fft) ++logn;
+  if (generic && ((1 << logn) != c.n_fft || c.n_fft < 256 || c.n_fft > 4096))
+    return fail(TTSA_ERR_UNSUPPORTED, "num_freq %d: n_fft = %d must be a power of two in [256, 4096]", c.num_freq, c.n_fft);
+  if (c.hop_length < 2 || c.win_length < c.hop_length || c.win_length > c.n_fft)
     return fail(TTSA_ERR_UNSUPPORTED, "need 2 <= hop_length <= win_length <= n_fft (hop %d, win %d)", c.hop_length, c.win_length);
-  if (c.win_length - c.hop_length > kNF * c.hop_length)
+  if (!generic && c.win_length - c.hop_length > kNF * c.hop_length)
     return fail(TTSA_ERR_UNSUPPORTED, "win_length %d > %d * hop_length %d", c.win_length, kNF + 1, c.hop_length);
   if (c.num_mels > kMtlMaxK) return fail(TTSA_ERR_UNSUPPORTED, "num_mels %d > %d", c.num_mels, kMtlMaxK);
   if (c.signal_norm && (c.max_norm <= 0 || c.min_level_db >= 0))
@@ -203,9 +303,10 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   ttsa_plan* p = new ttsa_plan();
   p->cfg = c;
   p->device = device;
+  p->generic = generic;
   build_geo(c, p->geo);
   p->nz = kernel_class(c);
-  if ((size_t)p->geo.ly.sm_total * 4 > 227 * 1024) {
+  if (!generic && (size_t)p->geo.ly.sm_total * 4 > 227 * 1024) {
     delete p;
     return fail(TTSA_ERR_UNSUPPORTED, "hop/win need %d bytes of shared memory per CTA", p->geo.ly.sm_total * 4);
   }
@@ -213,7 +314,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   // ---- host tables (float64) ----
   const double fmax = c.mel_fmax > 0 ? c.mel_fmax : 0.5 * c.sample_rate;
   p->h_mel = ttsa_host::mel_basis(c.sample_rate, c.n_fft, c.num_mels, c.mel_fmin, fmax);
-  p->h_inv_mel = ttsa_host::pinv_wide(p->h_mel, c.num_mels, kF);
+  p->h_inv_mel = ttsa_host::pinv_wide(p->h_mel, c.num_mels, c.num_freq);
 
   // elementwise parameter blocks
   p->pw.signal_norm = c.signal_norm; p->pw.symmetric_norm = c.symmetric_norm; p->pw.clip_norm = c.clip_norm;
@@ -227,7 +328,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   }
   mp.a_lo = p->geo.s_lo; mp.a_hi = p->geo.s_hi;
   mp.n_a = p->geo.n_a; mp.n_b = p->geo.n_b; mp.n_lo = p->geo.n_lo; mp.n_hi = p->geo.n_hi; mp.min_amp = p->geo.min_amp;
-  mp.power = (float)c.power; mp.num_mels = c.num_mels; mp.rows = 0;
+  mp.power = (float)c.power; mp.num_mels = c.num_mels; mp.F = c.num_freq; mp.rows = 0;
 
   if (device < 0) { *out = p; return TTSA_OK; }
 
@@ -245,6 +346,11 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     return fail(TTSA_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   }
   p->num_sms = prop.multiProcessorCount;
+  if (generic) {
+    if (int rc = plan_create_generic(p, logn)) { delete p; return rc; }
+    *out = p;
+    return TTSA_OK;
+  }
 
   const std::vector<double> w = ttsa_host::hann_periodic(c.win_length);
   std::vector<float> h_tw(2048), h_g(1024), h_wE(1024, 0.f), h_wO(1024, 0.f), h_wE2(1024, 0.f), h_wO2(1024, 0.f),
@@ -533,6 +639,7 @@ extern "C" int ttsa_stft_features(const ttsa_plan* plan, const ttsa_batch* batch
   FrameArgs a{};
   a.wav_in = wav_dev; a.lin_out = lin_out_dev; a.mel_out = mel_out_dev;
   a.preemph = (flags & TTSA_FEAT_PREEMPHASIS) ? 1 : 0;
+  if (plan->generic) return gen_launch(plan, batch, MODE_ANALYSIS, OUT_FEATURES, a, (cudaStream_t)stream);
   return launch_frames(plan, batch, MODE_ANALYSIS, OUT_FEATURES, false, a, (cudaStream_t)stream);
 }
 
@@ -542,6 +649,7 @@ extern "C" int ttsa_stft(const ttsa_plan* plan, const ttsa_batch* batch, const f
   DeviceGuard guard(plan->device);
   FrameArgs a{};
   a.wav_in = wav_dev; a.cplx_out = stft_out_dev;
+  if (plan->generic) return gen_launch(plan, batch, MODE_ANALYSIS, OUT_COMPLEX, a, (cudaStream_t)stream);
   return launch_frames(plan, batch, MODE_ANALYSIS, OUT_COMPLEX, false, a, (cudaStream_t)stream);
 }
 
@@ -551,6 +659,7 @@ extern "C" int ttsa_istft(const ttsa_plan* plan, const ttsa_batch* batch, const 
   DeviceGuard guard(plan->device);
   FrameArgs a{};
   a.cplx_in = stft_dev; a.wav_out = wav_out_dev; a.rows_total = batch->total_frames;
+  if (plan->generic) return gen_synthesise(plan, batch, MODE_SYNTH, SRC_COMPLEX, a, (cudaStream_t)stream);
   return launch_frames(plan, batch, MODE_SYNTH, SRC_COMPLEX, false, a, (cudaStream_t)stream);
 }
 
@@ -713,6 +822,20 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
   else        { bufs[iters & 1] = wav_out_dev; bufs[(iters & 1) ^ 1] = wsA; last = wav_out_dev; }
   if (sc_log_dev && iters > 0) CUDA_TRY(cudaMemsetAsync(sc_log_dev, 0, (size_t)iters * batch->B * 2 * 4, st));
 
+  if (plan->generic) {
+    FrameArgs a{};
+    a.spec = spec_dev; a.angles = init_angles_dev; a.seed = seed; a.wav_out = bufs[0];
+    if (int rc = gen_synthesise(plan, batch, MODE_SYNTH, spec_kind, a, st)) return rc;
+    for (int i = 1; i <= iters; ++i) {
+      FrameArgs b{};
+      b.spec = spec_dev; b.wav_in = bufs[(i - 1) & 1]; b.wav_out = bufs[i & 1];
+      b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
+      if (int rc = gen_synthesise(plan, batch, MODE_GL_ITER, spec_kind, b, st)) return rc;
+    }
+    if (bufs[iters & 1] != last) return fail(TTSA_ERR_CUDA, "internal: buffer rotation");
+    if (deemph) return deemph_launch(plan, batch, last, wav_out_dev, agg, st);
+    return TTSA_OK;
+  }
   FrameArgs a{};
   a.spec = spec_dev; a.spec_end = spec_dev + (size_t)batch->total_frames * kF; a.rows_total = batch->total_frames;
   a.angles = init_angles_dev; a.seed = seed; a.wav_out = bufs[0];
@@ -743,8 +866,8 @@ extern "C" int ttsa_mel_to_linear(const ttsa_plan* plan, const ttsa_batch* batch
   MelParams mp = plan->mel;
   mp.rows = batch->total_frames;
   const char* simt = std::getenv("TTSA_MEL_GEMM");
-  if (simt != nullptr && std::strcmp(simt, "simt") == 0) {      // fp32 SIMT reference kernel (profiling / cross-check)
-    dim3 grid((kF + kMtlBins - 1) / kMtlBins, (unsigned)((batch->total_frames + kMtlRows - 1) / kMtlRows));
+  if (plan->generic || (simt != nullptr && std::strcmp(simt, "simt") == 0)) {   // fp32 SIMT kernel (any num_freq; profiling / cross-check)
+    dim3 grid((mp.F + kMtlBins - 1) / kMtlBins, (unsigned)((batch->total_frames + kMtlRows - 1) / kMtlRows));
     const size_t smem = (size_t)mp.num_mels * (kMtlBins + kMtlRows) * 4;
     mel_to_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mp, plan->d_pinvT, plan->ldp, mel_dev, lin_out_dev, in_kind, out_kind);
   } else if (plan->d_pinv_tc96 != nullptr && !(simt != nullptr && std::strcmp(simt, "tc_simple") == 0)) {
@@ -780,7 +903,10 @@ extern "C" int ttsa_linear_to_mel(const ttsa_plan* plan, const ttsa_batch* batch
   MelParams mp = plan->mel;
   mp.rows = batch->total_frames;
   const char* simt = std::getenv("TTSA_MEL_GEMM");
-  if (plan->d_mel_tc == nullptr || (simt != nullptr && std::strcmp(simt, "simt") == 0)) {   // banded fp32 SIMT kernel
+  if (plan->generic) {
+    const unsigned grid = (unsigned)((batch->total_frames + 7) / 8);
+    gen_linear_to_mel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp, mp.F, plan->gt, lin_dev, mel_out_dev, in_kind, out_kind);
+  } else if (plan->d_mel_tc == nullptr || (simt != nullptr && std::strcmp(simt, "simt") == 0)) {   // banded fp32 SIMT kernel
     const unsigned grid = (unsigned)((batch->total_frames + 7) / 8);
     linear_to_mel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp, plan->tb, lin_dev, mel_out_dev, in_kind, out_kind);
   } else {
