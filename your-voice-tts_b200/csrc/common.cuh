@@ -64,6 +64,8 @@ __host__ __device__ constexpr Layout make_layout(int hop, int win, int nz) {
 struct Geo {
   Layout ly;
   int num_mels;
+  int mel_smem_floats;       // > 0: the compact mel basis (Tables::mel_compact) fits behind Layout::sm_total in the
+                             //      feature kernel's shared memory; 0: read the banded basis from global memory
   // spectrogram value -> magnitude:  S = exp2(c1 * clip(x, lo, hi) + c0)   (denormalize, +ref, db_to_amp, **power fused)
   float s_c1, s_c0, s_lo, s_hi;
   // amplitude -> normalised dB:      v = clip(n_a * log2(max(min_amp, a)) + n_b, n_lo, n_hi)
@@ -87,6 +89,8 @@ struct Tables {
   const int* mel_cnt;    // [num_mels]
   const float* mel_val;  // [num_mels * mel_ld]
   int mel_ld;
+  // the same basis without padding: int2 (first tap index in mel_cval, first bin) per filter, one extra entry, then the taps
+  const float* mel_compact;
 };
 
 // Batch layout on the device.

@@ -140,6 +140,11 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float2 shfl2(float a, float b, int srclane) {
   return make_float2(__shfl_sync(0xffffffffu, a, srclane), __shfl_sync(0xffffffffu, b, srclane));
 }
@@ -188,6 +193,9 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
                  ::"r"(dst), "l"(tb.smem_image), "r"(bytes), "r"(mbar) : "memory");
   }
   for (int i = tid; i < ly.plane_len; i += kThreads) { plane0[i] = 0.0f; plane1[i] = 0.0f; }
+  if constexpr (MODE == MODE_ANALYSIS && SRC == OUT_FEATURES) {
+    for (int i = tid; i < g.mel_smem_floats; i += kThreads) smem[ly.sm_total + i] = tb.mel_compact[i];
+  }
   __syncthreads();                                 // the mbarrier is initialised for everyone
   {
     unsigned done = 0;
@@ -573,16 +581,16 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               cout[1024 - k0] = cmul(make_float2(XpR.x, XpI.x), shift_phasor(1024 - k0, lpad, -1.0f));
               cout[992 - k0] = cmul(make_float2(XpR.y, XpI.y), shift_phasor(992 - k0, lpad, -1.0f));
             } else {
-              magbuf[k0] = sqrtf(XkR.x * XkR.x + XkI.x * XkI.x);
-              magbuf[k0 + 32] = sqrtf(XkR.y * XkR.y + XkI.y * XkI.y);
-              magbuf[1024 - k0] = sqrtf(XpR.x * XpR.x + XpI.x * XpI.x);
-              magbuf[992 - k0] = sqrtf(XpR.y * XpR.y + XpI.y * XpI.y);
+              magbuf[k0] = sqrt_fast(XkR.x * XkR.x + XkI.x * XkI.x);
+              magbuf[k0 + 32] = sqrt_fast(XkR.y * XkR.y + XkI.y * XkI.y);
+              magbuf[1024 - k0] = sqrt_fast(XpR.x * XpR.x + XpI.x * XpI.x);
+              magbuf[992 - k0] = sqrt_fast(XpR.y * XpR.y + XpI.y * XpI.y);
             }
           });
           if (l0) {   // k = 512: X = conj(Z[512])
             const float2 Xc = make_float2(R[8].x, -I[8].x);
             if constexpr (SRC == OUT_COMPLEX) cout[512] = cmul(Xc, shift_phasor(512, lpad, -1.0f));
-            else magbuf[512] = sqrtf(Xc.x * Xc.x + Xc.y * Xc.y);
+            else magbuf[512] = sqrt_fast(Xc.x * Xc.x + Xc.y * Xc.y);
           }
           if constexpr (SRC == OUT_FEATURES) {
             __syncwarp();
@@ -592,12 +600,27 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
             }
             if (a.mel_out != nullptr) {
               float* out = a.mel_out + row * g.num_mels;
-              for (int m = lane; m < g.num_mels; m += 32) {
-                const int lo = tb.mel_lo[m], cnt = tb.mel_cnt[m];
-                const float* mv = tb.mel_val + m * tb.mel_ld;
-                float acc = 0.0f;
-                for (int c = 0; c < cnt; ++c) acc = fmaf(__ldg(mv + c), magbuf[lo + c], acc);
-                out[m] = amp_to_norm_db(acc, g);
+              if (g.mel_smem_floats > 0) {
+                // compact basis in shared memory: (first tap, first bin) per filter, then the taps
+                const int2* mdesc = reinterpret_cast<const int2*>(smem + ly.sm_total);
+                const float* mval = smem + ly.sm_total + 2 * (g.num_mels + 1);
+                for (int m = lane; m < g.num_mels; m += 32) {
+                  const int2 d0 = mdesc[m];
+                  const int cnt = mdesc[m + 1].x - d0.x;
+                  const float* mv = mval + d0.x;
+                  const float* mg = magbuf + d0.y;
+                  float acc = 0.0f;
+                  for (int c = 0; c < cnt; ++c) acc = fmaf(mv[c], mg[c], acc);
+                  out[m] = amp_to_norm_db(acc, g);
+                }
+              } else {
+                for (int m = lane; m < g.num_mels; m += 32) {
+                  const int lo = tb.mel_lo[m], cnt = tb.mel_cnt[m];
+                  const float* mv = tb.mel_val + m * tb.mel_ld;
+                  float acc = 0.0f;
+                  for (int c = 0; c < cnt; ++c) acc = fmaf(__ldg(mv + c), magbuf[lo + c], acc);
+                  out[m] = amp_to_norm_db(acc, g);
+                }
               }
             }
           }

@@ -22,8 +22,10 @@ const char* launch_synth(int src, int nz, bool fixed, int grid, size_t smem, cud
 const char* launch_analysis(int out, int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 
 template <class K>
-inline const char* set_smem(K kernel, size_t smem_bytes) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+inline const char* set_smem(K kernel, size_t /*smem_bytes*/) {
+  // The attribute belongs to the function, not to a plan: opt in to the device maximum (227 KB on sm_100) once, so that
+  // plans with different geometries can share the kernels; each launch still requests only what its plan needs.
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

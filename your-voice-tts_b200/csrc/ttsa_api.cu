@@ -412,6 +412,24 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   for (int k = 0; k < kF; ++k)
     for (int m = 0; m < c.num_mels; ++m) h_pinvT[(size_t)m * p->ldp + k] = (float)p->h_inv_mel[(size_t)k * c.num_mels + m];
 
+  // compact copy of the banded basis for the feature kernel's shared memory: int2 (first tap, first bin) per filter
+  // (+ one end entry), then the taps back to back; used when it fits beside the frame buffers with 2 CTAs per SM
+  std::vector<float> h_melc;
+  {
+    std::vector<int> desc(2 * (c.num_mels + 1), 0);
+    std::vector<float> taps;
+    for (int m = 0; m < c.num_mels; ++m) {
+      desc[2 * m] = (int)taps.size(); desc[2 * m + 1] = h_lo[m];
+      for (int cidx = 0; cidx < h_cnt[m]; ++cidx) taps.push_back(h_val[(size_t)m * ld + cidx]);
+    }
+    desc[2 * c.num_mels] = (int)taps.size();
+    h_melc.resize(desc.size() + taps.size());
+    std::memcpy(h_melc.data(), desc.data(), desc.size() * 4);
+    std::memcpy(h_melc.data() + desc.size(), taps.data(), taps.size() * 4);
+    const size_t per_cta_limit = (233472 - 2 * 1024) / 2;          // two CTAs per SM, 1 KB reserved each
+    const bool fits = ((size_t)ly.sm_total + h_melc.size()) * 4 <= per_cta_limit;
+    p->geo.mel_smem_floats = fits ? (int)h_melc.size() : 0;
+  }
   p->pinv_chunks = (c.num_mels + kTcChunk - 1) / kTcChunk;
   const std::vector<uint16_t> h_pinv_tc = canon_split_b(p->h_inv_mel, kF, c.num_mels, 208, 5, p->pinv_chunks);
   std::vector<uint16_t> h_mel_tc;
@@ -426,7 +444,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       {h_cnt.data(), h_cnt.size() * 4, 0}, {h_val.data(), h_val.size() * 4, 0}, {h_pinvT.data(), h_pinvT.size() * 4, 0},
       {h_wE2.data(), h_wE2.size() * 4, 0}, {h_wO2.data(), h_wO2.size() * 4, 0},
       {h_pinv_tc.data(), h_pinv_tc.size() * 2, 0}, {h_mel_tc.data(), h_mel_tc.size() * 2, 0},
-      {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}, {h_img.data(), h_img.size() * 4, 0}};
+      {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}, {h_img.data(), h_img.size() * 4, 0},
+      {h_melc.data(), h_melc.size() * 4, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -446,6 +465,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->d_mel_tc = h_mel_tc.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[12].off);
   p->d_pinv_tc96 = h_pinv_tc96.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[13].off);
   p->tb.smem_image = (const float*)(base + pieces[14].off);
+  p->tb.mel_compact = (const float*)(base + pieces[15].off);
   p->tb.wE = (const float*)(base + pieces[2].off);
   p->tb.wO = (const float*)(base + pieces[3].off);
   p->tb.pw = (const float*)(base + pieces[4].off);
@@ -456,7 +476,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->d_pinvT = (const float*)(base + pieces[8].off);
 
   // configure every kernel once (dynamic shared memory opt-in, occupancy), outside any stream capture
-  const size_t smem_bytes = (size_t)p->geo.ly.sm_total * 4;
+  const size_t smem_bytes = ((size_t)p->geo.ly.sm_total + p->geo.mel_smem_floats) * 4;   // the feature kernel's request
   int occ = 0;
   const char* err = configure_frame_kernels(smem_bytes, &occ);
   if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
@@ -623,7 +643,8 @@ static int launch_frames(const ttsa_plan* plan, const ttsa_batch* batch, int mod
   if (batch->dev.total_tiles == 0) return TTSA_OK;
   const int max_ctas = plan->ctas_per_sm * plan->num_sms;
   const int grid = batch->dev.total_tiles < max_ctas ? batch->dev.total_tiles : max_ctas;
-  const char* err = launch_frame_kernel(mode, src, plan->nz, sc, plan->fixed_geo, grid, (size_t)plan->geo.ly.sm_total * 4, st,
+  const size_t smem = ((size_t)plan->geo.ly.sm_total + ((mode == MODE_ANALYSIS && src == OUT_FEATURES) ? plan->geo.mel_smem_floats : 0)) * 4;
+  const char* err = launch_frame_kernel(mode, src, plan->nz, sc, plan->fixed_geo, grid, smem, st,
                                         plan->geo, plan->tb, batch->dev, args);
   if (err) return fail(TTSA_ERR_CUDA, "frame kernel launch (mode %d): %s", mode, err);
   return TTSA_OK;
