@@ -389,6 +389,16 @@ def test_host_pipeline_matches_direct_calls():
         for u in range(len(Ts)):
             a, b = lay.split_wav(outs[i])[u], lay.split_wav(ref)[u]
             assert torch.equal(a, b)
+    # the same pipeline replaying one CUDA graph per buffer set: the seed of each set is the one of its first batch
+    outs_g = [torch.empty((lay.total_samples,), dtype=torch.float32).pin_memory() for _ in range(4)]
+    pipe_g = HostPipeline(ap, lay, graph=True)
+    for i in range(4):
+        pipe_g.submit(mels[i], outs_g[i], seed=10 + i)
+    pipe_g.drain()
+    for i in range(4):
+        ref = ap.inv_mel_spectrogram_batch(mels[i].cuda(), lay, seed=10 + (i & 1)).cpu()
+        for u in range(len(Ts)):
+            assert torch.equal(lay.split_wav(outs_g[i])[u], lay.split_wav(ref)[u])
 
 
 def test_feature_extraction_training_batch_cfg3():

@@ -98,34 +98,68 @@ class BatchLayout(object):
 class HostPipeline(object):
     """Host-to-host batched inv_mel_spectrogram with the copies hidden behind the compute of neighbouring batches.
 
-    submit(mel_host, wav_host, seed) enqueues: pinned-host mel -> device (compute stream), mel -> linear ->
-    Griffin-Lim -> de-emphasis (compute stream), device waveform -> pinned host (copy stream).  Two device buffer sets
-    alternate, so the D2H copy of batch i overlaps the kernels of batch i+1.  `wav_host` is valid after the returned
+    submit(mel_host, wav_host, seed) enqueues: pinned-host mel -> device (upload stream), mel -> linear ->
+    Griffin-Lim -> de-emphasis (compute stream), device waveform -> pinned host (download stream).  Two device buffer
+    sets alternate, so the upload of batch i+1 and the download of batch i-1 overlap the kernels of batch i.  `wav_host` is valid after the returned
     event (or drain())."""
 
-    def __init__(self, ap, layout):
+    def __init__(self, ap, layout, graph=False):
+        """graph=True replays the kernels of a batch (mel -> linear, initial synthesis, the Griffin-Lim iterations,
+        de-emphasis) as one CUDA graph per buffer set instead of ~65 individual launches; the Philox seed of the initial
+        phases is then the one given at the first submit() of each buffer set."""
         torch = _torch()
         self.ap, self.layout = ap, layout
         dev = ap._dev()
-        self.comp, self.copy = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.comp, self.copy, self.h2d = (torch.cuda.Stream(device=dev) for _ in range(3))
         n = max(1, layout.total_samples)
         self.mel_dev = [torch.empty((layout.total_frames, ap.num_mels), dtype=torch.float32, device=dev) for _ in range(2)]
         self.wav_dev = [torch.zeros((n,), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.lin_dev = torch.empty((max(1, layout.total_frames), ap.num_freq), dtype=torch.float32, device=dev)
         ws_bytes = int(layout.plan.lib.ttsa_griffin_lim_workspace_bytes(layout.plan.handle, layout.handle))
         self.ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         self.comp_done = [torch.cuda.Event() for _ in range(2)]
         self.copy_done = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
         self.count = 0
+        self.use_graph = bool(graph)
+        self.graphs = [None, None]
+
+    def _compute(self, b, seed):
+        """mel -> |S|^power -> Griffin-Lim -> de-emphasis of buffer set b on the current stream."""
+        ap, lay = self.ap, self.layout
+        plan = lay.plan
+        st = ap._stream()
+        L.check(plan.lib.ttsa_mel_to_linear(plan.handle, lay.handle, ap._ptr(self.mel_dev[b]), L.MEL_IN_NORM_DB,
+                                            ap._ptr(self.lin_dev), L.MEL_OUT_POWER, st))
+        L.check(plan.lib.ttsa_griffin_lim(plan.handle, lay.handle, ap._ptr(self.lin_dev), L.SPEC_MAGNITUDE,
+                                          int(ap.griffin_lim_iters), None, ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                          L.GL_DEEMPHASIS if ap.preemphasis != 0 else 0, ap._ptr(self.wav_dev[b]), None,
+                                          ap._ptr(self.ws), self.ws.numel(), st))
 
     def submit(self, mel_host, wav_host, seed=0):
         torch = _torch()
         b = self.count & 1
+        if self.use_graph and self.graphs[b] is None:
+            with torch.cuda.stream(self.comp):
+                self._compute(b, seed)                          # warm-up outside capture
+            self.comp.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.comp):
+                self._compute(b, seed)
+            self.graphs[b] = g
+        with torch.cuda.stream(self.h2d):
+            if self.count >= 2:
+                self.h2d.wait_event(self.comp_done[b])         # batch i-2 has consumed this mel buffer
+            self.mel_dev[b].copy_(mel_host, non_blocking=True)  # overlaps the kernels of batch i-1
+            self.h2d_done[b].record(self.h2d)
         with torch.cuda.stream(self.comp):
             if self.count >= 2:
-                self.comp.wait_event(self.copy_done[b])        # the buffers of batch i-2 have been drained
-            self.mel_dev[b].copy_(mel_host, non_blocking=True)
-            self.ap.inv_mel_spectrogram_batch(self.mel_dev[b], self.layout, seed=seed, out=self.wav_dev[b],
-                                              workspace=self.ws)
+                self.comp.wait_event(self.copy_done[b])        # the waveform buffer of batch i-2 has been drained
+            self.comp.wait_event(self.h2d_done[b])
+            if self.use_graph:
+                self.graphs[b].replay()
+            else:
+                self._compute(b, seed)
             self.comp_done[b].record(self.comp)
         with torch.cuda.stream(self.copy):
             self.copy.wait_event(self.comp_done[b])
@@ -135,6 +169,7 @@ class HostPipeline(object):
         return self.copy_done[b]
 
     def drain(self):
+        self.h2d.synchronize()
         self.comp.synchronize()
         self.copy.synchronize()
 
