@@ -84,9 +84,11 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.windows = index, None, [], []
 
     def start(self):
+        """Started before the warm-up (nvidia-smi needs ~0.1 s to produce its first line); only samples that fall
+        inside a begin()/end() window -- the timed regions -- are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
@@ -98,33 +100,52 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        if self.windows and self.windows[-1][1] is None:
+            self.windows[-1][1] = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0])); mx = float(parts[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+
+        def collect(pred):
+            sm, mx, reasons = [], None, set()
+            for t, ln in self.lines:
+                if not pred(t):
+                    continue
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    sm.append(float(parts[0])); mx = float(parts[1])
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sm, mx, reasons
+
+        wins = [(a, b if b is not None else float("inf")) for a, b in self.windows]
+        sm, mx, reasons = collect(lambda t: any(a <= t <= b + 0.03 for a, b in wins))
+        window = "timed regions"
+        if not sm and wins:            # timed regions shorter than the sampling period: the GPU has been under the same
+            sm, mx, reasons = collect(lambda t: t >= wins[0][0] - 1.0)    # load since the warm-up; use those samples
+            window = "warm-up + timed regions"
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -291,11 +312,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ("value") ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         run_step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin()
     launches0 = int(lib.ttsa_launch_count())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -308,7 +330,7 @@ def main():
     if graph is not None:
         launches = launches_per_step * args.steps          # replayed from the captured graph
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    sampler.end()
     t_ms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -327,6 +349,7 @@ def main():
         pipe.submit(mel_host, wav_hosts[i & 1], seed=1 + i)
     pipe.drain()
     barrier()
+    sampler.begin()
     t0 = time.perf_counter()
     with torch.cuda.stream(pipe.h2d):
         e0.record(pipe.h2d)                                 # before the first host -> device copy
@@ -337,6 +360,8 @@ def main():
     pipe.drain()
     barrier()
     wall = time.perf_counter() - t0
+    sampler.end()
+    clocks = sampler.stop()
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
     assert float(wav_hosts[(args.steps - 1) & 1].abs().max()) > 0.0   # the waveform really arrived on the host
     t_e = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
