@@ -206,12 +206,10 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     }
   }
 
-  // programmatic dependent launch: let the next kernel on the stream begin its prologue, and wait here until the
-  // previous kernel's global writes (the waveform this kernel reads, the buffer it overwrites) are complete
+  // contiguous tile range of this CTA over the flattened (utterance, tile) list.  Everything that depends only on
+  // the batch layout and the (constant) spectrogram happens BEFORE the dependency wait below: the utterance search is a
+  // chain of dependent global loads, and the first tile's |S| rows can already travel towards L2.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  // contiguous tile range of this CTA over the flattened (utterance, tile) list
   const long long tile_lo = (long long)blockIdx.x * bd.total_tiles / gridDim.x;
   const long long tile_hi = (long long)(blockIdx.x + 1) * bd.total_tiles / gridDim.x;
   int u = 0;
@@ -223,6 +221,18 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     }
     u = lo;
   }
+  if constexpr (MODE == MODE_GL_ITER) {
+    if (tile_lo < tile_hi) {
+      const int t_first = (int)(tile_lo - bd.tile_off[u]) * kNF;
+      const int n_rows = min(kNF, bd.T[u] - t_first);
+      const char* rows = reinterpret_cast<const char*>(a.spec + (bd.frame_off[u] + t_first) * kF);
+      const int bytes = n_rows * kF * 4;
+      for (int o = tid * 128; o < bytes; o += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + o));
+    }
+  }
+  // programmatic dependent launch: wait here until the previous kernel's global writes (the waveform this kernel
+  // reads, the buffer it overwrites) are complete
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   long long tile = tile_lo;
   while (tile < tile_hi) {
