@@ -6,6 +6,7 @@ import pytest
 
 from conftest import MAIN_AUDIO, TEST_AUDIO, run_reference_test_normalize, snr_db, synth_speech_like
 from oracle.audio_oracle import OracleAudioProcessor, lfilter_fir2, lfilter_iir1, lr_istft, lr_stft
+from your_voice_tts_b200 import _lib as L
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -551,3 +552,55 @@ def test_other_num_freq_any_size_path(nf_flm_fsm):
     out = ap.inv_spectrogram_batch(specs, lay, seed=3)
     assert all(torch.isfinite(o).all() for o in lay.split_wav(out))
     assert [int(o.numel()) for o in lay.split_wav(out)] == [hop * max(0, t - 1) for t in Ts]
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties_64x6s():
+    """BASELINE configs[1]/[2] sizes (64 utterances x 132 300 samples, 482 frames), checked through size-independent
+    properties: istft(stft(y)) == y on the samples librosa returns; the STFT is linear; a consistent spectrogram with
+    its own phases is a fixed point of the Griffin-Lim iteration (the projection leaves it unchanged), whatever the
+    number of iterations; and the batched features equal the per-utterance call."""
+    ap = _ap(dict(MAIN_AUDIO, griffin_lim_iters=3))
+    B, Lw = 64, 132300
+    lay = ap.layout(wav_lengths=[Lw] * B)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    wav = torch.zeros((lay.total_samples,), device="cuda")
+    t = torch.arange(Lw, device="cuda", dtype=torch.float32) / 22050.0
+    for u in range(B):
+        f0 = 90.0 + 3.0 * u
+        wav[int(lay.wav_off[u]):int(lay.wav_off[u]) + Lw] = 0.4 * torch.sin(2 * np.pi * f0 * t) * (0.6 + 0.4 * torch.sin(2 * np.pi * 1.7 * t)) \
+            + 0.01 * torch.randn((Lw,), device="cuda", generator=g)
+    D = ap.stft_batch(wav, lay)                                   # [sum_T, 1025, 2]
+    assert D.shape == (B * 482, 1025, 2)
+    y = ap.istft_batch(D, lay)
+    for u in (0, 31, 63):
+        a = wav[int(lay.wav_off[u]):int(lay.wav_off[u]) + 275 * 481]
+        b = y[int(lay.wav_off[u]):int(lay.wav_off[u]) + 275 * 481]
+        assert snr_db(a.cpu().numpy(), b.cpu().numpy()) >= 100.0
+    # linearity
+    wav2 = torch.roll(wav, 12345) * 0.5
+    D2 = ap.stft_batch(wav2, lay)
+    D12 = ap.stft_batch(wav + wav2, lay)
+    assert float((D12 - (D + D2)).abs().max()) <= 2e-5 * float(D12.abs().max())
+    # fixed point: take y' = istft(D) (hop*(T-1) samples, so that stft and istft are exact inverses on it); |stft(y')|
+    # with the phases of stft(y') reproduces y' after any number of iterations, with spectral convergence ~ 0
+    Lf = 275 * 481
+    lay_f = ap.layout(n_frames=[482] * B)
+    lay_w = ap.layout(wav_lengths=[Lf] * B)
+    yp = torch.zeros((lay_w.total_samples,), device="cuda")
+    for u in range(B):
+        yp[int(lay_w.wav_off[u]):int(lay_w.wav_off[u]) + Lf] = y[int(lay.wav_off[u]):int(lay.wav_off[u]) + Lf]
+    Dp = ap.stft_batch(yp, lay_w)
+    mag = torch.sqrt(Dp[..., 0] ** 2 + Dp[..., 1] ** 2).contiguous()
+    ang = torch.atan2(Dp[..., 1], Dp[..., 0]).contiguous()
+    yg, sc = ap.griffin_lim_batch(mag, lay_f, L.SPEC_MAGNITUDE, init_angles=ang, return_sc=True)
+    assert float(sc.max()) <= 1e-4, float(sc.max())
+    for u in (0, 40, 63):
+        a = yp[int(lay_w.wav_off[u]):int(lay_w.wav_off[u]) + Lf].cpu().numpy()
+        b = lay_f.split_wav(yg)[u].cpu().numpy()
+        assert snr_db(a, b) >= 80.0, snr_db(a, b)
+    # batched features == single-utterance features
+    lin, mel = ap.features_batch(wav, lay)
+    one = wav[int(lay.wav_off[5]):int(lay.wav_off[5]) + Lw].cpu().numpy()
+    np.testing.assert_allclose(lin[5 * 482:6 * 482].cpu().numpy().T, ap.spectrogram(one), atol=1e-6)
+    np.testing.assert_allclose(mel[5 * 482:6 * 482].cpu().numpy().T, ap.melspectrogram(one), atol=1e-6)
