@@ -195,7 +195,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_tc_kernel(const TcG
         float x = __uint_as_float(v[i]);
         if (p.mode == 0) {
           x = fmaxf(1e-10f, x);
-          if (p.out_kind == 1) x = pow15 ? x * sqrtf(x) : exp2f(p.mp.power * log2f(x));
+          if (p.out_kind == 1) {
+          if (pow15) {                         // x ** 1.5 (the shipped `power`): x * sqrt(x), sqrt.approx is ~1 ulp
+            float sq;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(x));
+            x *= sq;
+          } else {
+            x = exp2f(p.mp.power * log2f(x));
+          }
+        }
         } else if (p.out_kind == 2) {
           x = fmaf(p.mp.n_a, log2f(fmaxf(p.mp.min_amp, x)), p.mp.n_b);
           x = fminf(fmaxf(x, p.mp.n_lo), p.mp.n_hi);
@@ -308,17 +316,31 @@ __global__ void __launch_bounds__(kM2lThreads, 1) mel_to_linear_tc_kernel(const 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float x = fmaxf(1e-10f, __uint_as_float(v[i]));
-        if (p.out_kind == 1) x = pow15 ? x * sqrtf(x) : exp2f(p.mp.power * log2f(x));
+        if (p.out_kind == 1) {
+          if (pow15) {                         // x ** 1.5 (the shipped `power`): x * sqrt(x), sqrt.approx is ~1 ulp
+            float sq;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(x));
+            x *= sq;
+          } else {
+            x = exp2f(p.mp.power * log2f(x));
+          }
+        }
         stage[r * kM2lStageLd + cc * 8 + i] = x;
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     const int col0 = nt * kM2lN;
-    for (int idx = tid; idx < kTcRows * kM2lN; idx += kM2lThreads) {
-      const int rr = idx / kM2lN, c = idx - rr * kM2lN;
+    // warp w stores rows w, w + 16, ...; its lanes cover the 96 columns in three 128-byte pieces
+    static_assert(kM2lN == 96 && kM2lThreads == 512, "store mapping below assumes 96 columns and 16 warps");
+    for (int rr = warp; rr < kTcRows; rr += kM2lThreads / 32) {
       const long long row = row0 + rr;
-      if (row < p.mp.rows && col0 + c < p.n_valid) p.out[row * p.ldo + col0 + c] = stage[rr * kM2lStageLd + c];
+      if (row >= p.mp.rows) break;
+      float* orow = p.out + row * p.ldo + col0;
+      const float* srow = stage + rr * kM2lStageLd;
+#pragma unroll
+      for (int c = lane; c < kM2lN; c += 32)
+        if (col0 + c < p.n_valid) orow[c] = srow[c];
     }
   };
 
