@@ -145,6 +145,15 @@ int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, const float
                      float* wav_out_dev, float* sc_log_dev, void* workspace_dev, size_t workspace_bytes,
                      void* stream);
 
+/* Fast Griffin-Lim (Perraudin, Balazs, Sondergaard 2013; librosa >= 0.7 griffinlim(momentum=...)).  NOT in the
+ * reference -- it changes the result, so it is a separate, opt-in entry point: iteration i takes the phases of
+ * stft(y_{i-1}) - momentum / (1 + momentum) * stft(y_{i-2}) (y_{-1} = 0), i.e. the kernel transforms
+ * y_{i-1} - beta * y_{i-2} (the STFT is linear).  momentum in [0, 1); 0 is ttsa_griffin_lim exactly. */
+int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* batch, const float* spec_dev, int spec_kind,
+                          int iters, const float* init_angles_dev, uint64_t seed, uint32_t flags, double momentum,
+                          float* wav_out_dev, float* sc_log_dev, void* workspace_dev, size_t workspace_bytes,
+                          void* stream);
+
 /* ---- mel <-> linear (the dense contraction) --------------------------------------------- */
 #define TTSA_MEL_IN_AMPLITUDE 0  /* input already amplitude                                            */
 #define TTSA_MEL_IN_NORM_DB   1  /* input is normalised dB: _denormalize, +ref, _db_to_amp fused on load */

@@ -364,6 +364,33 @@ class OracleAudioProcessor(object):
             return y, np.asarray(sc)
         return y
 
+    # NOT in the reference: fast Griffin-Lim (Perraudin, Balazs, Sondergaard 2013) as librosa >= 0.7 implements it in
+    # griffinlim(momentum=...); kept here as the checker of the product's opt-in momentum mode.
+    def _griffin_lim_fast(self, S, momentum=0.99, init_angles=None, return_sc=False):
+        """angles_i = angle(rebuilt_i - momentum / (1 + momentum) * rebuilt_{i-1}), rebuilt_i = stft(istft(S * angles_{i-1})),
+        rebuilt_0 = 0; returns istft(S * angles_iters).  momentum = 0 is utils/audio.py:182-189 exactly.
+        ``return_sc``: || |rebuilt_i - beta * rebuilt_{i-1}| - |S| ||_F / ||S||_F per iteration."""
+        S = np.asarray(S, dtype=np.float64)
+        if init_angles is None:
+            init_angles = 2.0 * np.pi * np.random.rand(*S.shape)
+        angles = np.exp(1j * np.asarray(init_angles, dtype=np.float64))
+        S_complex = np.abs(S).astype(np.complex128)
+        beta = momentum / (1.0 + momentum)
+        rebuilt = 0.0
+        sc = []
+        for _ in range(self.griffin_lim_iters):
+            tprev = rebuilt
+            y = self._istft(S_complex * angles)
+            rebuilt = self._stft(y)
+            mixed = rebuilt - beta * tprev
+            if return_sc:
+                sc.append(spectral_convergence(np.abs(mixed), np.abs(S)))
+            angles = np.exp(1j * np.angle(mixed))
+        y = self._istft(S_complex * angles)
+        if return_sc:
+            return y, np.asarray(sc)
+        return y
+
     # utils/audio.py:154-162
     def inv_spectrogram(self, spectrogram, init_angles=None, return_sc=False):
         S = self._denormalize(np.asarray(spectrogram, dtype=np.float64))

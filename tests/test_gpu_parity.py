@@ -604,3 +604,51 @@ def test_full_size_properties_64x6s():
     one = wav[int(lay.wav_off[5]):int(lay.wav_off[5]) + Lw].cpu().numpy()
     np.testing.assert_allclose(lin[5 * 482:6 * 482].cpu().numpy().T, ap.spectrogram(one), atol=1e-6)
     np.testing.assert_allclose(mel[5 * 482:6 * 482].cpu().numpy().T, ap.melspectrogram(one), atol=1e-6)
+
+
+def test_fast_griffin_lim_momentum_opt_in():
+    """Fast Griffin-Lim (momentum; not in the reference, opt-in): the waveform-domain momentum of the kernels equals
+    the oracle's STFT-domain restatement of librosa's griffinlim(momentum=...), momentum 0 is the reference algorithm
+    bit for bit, and with momentum the spectral error after the same number of iterations is lower."""
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=12)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    y = synth_speech_like(31, n_samples=275 * 60)
+    S = np.abs(lr_stft(y.astype(np.float64), 2048, 275, 1102)).astype(np.float32)
+    ang = (2 * np.pi * np.random.default_rng(4).random(S.shape)).astype(np.float32)
+    dev = torch.device("cuda")
+    St = torch.from_numpy(np.ascontiguousarray(S.T)).to(dev)
+    At = torch.from_numpy(np.ascontiguousarray(ang.T)).to(dev)
+    lay = ap.layout(n_frames=[S.shape[1]])
+    n = 275 * (S.shape[1] - 1)
+    w0 = ap.griffin_lim_batch(St, lay, L.SPEC_MAGNITUDE, init_angles=At)[:n].clone()
+    w00 = ap.griffin_lim_batch(St, lay, L.SPEC_MAGNITUDE, init_angles=At, momentum=0.0)[:n].clone()
+    assert torch.equal(w0, w00)
+    for mom in (0.5, 0.99):
+        w, sc = ap.griffin_lim_batch(St, lay, L.SPEC_MAGNITUDE, init_angles=At, momentum=mom, return_sc=True)
+        wo, sco = orc._griffin_lim_fast(S, mom, init_angles=ang, return_sc=True)
+        assert snr_db(wo, w[:n].cpu().numpy()) >= GL_SNR_DB, (mom, snr_db(wo, w[:n].cpu().numpy()))
+        np.testing.assert_allclose(sc[:, 0].cpu().numpy(), sco, rtol=SC_RTOL)
+    # faster convergence: consistency error of the result after 12 iterations
+    err = lambda wav: spectral_err(np.abs(lr_stft(np.asarray(wav, dtype=np.float64), 2048, 275, 1102)), S)
+    def spectral_err(a, b):
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    e_plain = err(w0.cpu().numpy())
+    e_fast = err(ap.griffin_lim_batch(St, lay, L.SPEC_MAGNITUDE, init_angles=At, momentum=0.99)[:n].cpu().numpy())
+    assert e_fast < e_plain, (e_fast, e_plain)
+    # the attribute switches the drop-in methods, the any-size path follows the same definition
+    ap_f = _ap(dict(audio, griffin_lim_momentum=0.99))
+    spec_n = orc.spectrogram(y).astype(np.float32)
+    wf = ap_f.inv_spectrogram(spec_n, init_angles=ang)
+    Sn = orc._db_to_amp(orc._denormalize(spec_n.astype(np.float64)) + orc.ref_level_db) ** orc.power
+    wfo = orc.apply_inv_preemphasis(orc._griffin_lim_fast(Sn, 0.99, init_angles=ang))
+    assert snr_db(wfo, wf) >= GL_SNR_DB
+    audio_g = dict(MAIN_AUDIO, num_freq=513, frame_length_ms=40.0, frame_shift_ms=10.0, griffin_lim_iters=8)
+    apg, orcg = _ap(audio_g), OracleAudioProcessor(**audio_g)
+    yg = synth_speech_like(32, n_samples=orcg.hop_length * 40)
+    Sg = np.abs(lr_stft(yg.astype(np.float64), orcg.n_fft, orcg.hop_length, orcg.win_length)).astype(np.float32)
+    angg = (2 * np.pi * np.random.default_rng(5).random(Sg.shape)).astype(np.float32)
+    layg = apg.layout(n_frames=[Sg.shape[1]])
+    wg = apg.griffin_lim_batch(torch.from_numpy(np.ascontiguousarray(Sg.T)).to(dev), layg, L.SPEC_MAGNITUDE,
+                               init_angles=torch.from_numpy(np.ascontiguousarray(angg.T)).to(dev), momentum=0.9)
+    wgo = orcg._griffin_lim_fast(Sg, 0.9, init_angles=angg)
+    assert snr_db(wgo, wg[:len(wgo)].cpu().numpy()) >= GL_SNR_DB

@@ -55,6 +55,8 @@ PROTOTYPES = {
     "ttsa_griffin_lim_workspace_bytes": (c_size_t, [c_void_p, c_void_p]),
     "ttsa_griffin_lim": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_uint64, c_uint32, c_void_p,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ttsa_griffin_lim_fast": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_uint64, c_uint32, c_double,
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ttsa_mel_to_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "ttsa_linear_to_mel": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "ttsa_preemphasis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -223,6 +223,9 @@ class AudioProcessor(object):
                 print(" | > {}:{}".format(key, value))
         self._device = device
         self._batch_cache = OrderedDict()
+        # extension (not a reference field, so it is set after the member print-out): > 0 switches every inversion to
+        # fast Griffin-Lim with that momentum; 0 keeps the reference's algorithm
+        self.griffin_lim_momentum = float(kwargs.get("griffin_lim_momentum", 0.0))
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _stft_parameters(self):
@@ -361,9 +364,11 @@ class AudioProcessor(object):
         return out
 
     def griffin_lim_batch(self, spec_packed, layout, spec_kind=L.SPEC_MAGNITUDE, init_angles=None, seed=0,
-                          deemphasis=False, return_sc=False, iters=None, out=None, workspace=None):
+                          deemphasis=False, return_sc=False, iters=None, out=None, workspace=None, momentum=None):
         """_griffin_lim over a packed batch (utils/audio.py:182-189).  Returns the packed waveform buffer
-        (and, with return_sc, the [iters, B] spectral-convergence log)."""
+        (and, with return_sc, the [iters, B] spectral-convergence log).
+        momentum (default: self.griffin_lim_momentum, 0 = the reference's algorithm) > 0 selects fast Griffin-Lim
+        as in librosa >= 0.7 griffinlim(momentum=...): not in the reference, opt-in, changes the result."""
         torch = _torch()
         plan = layout.plan
         iters = int(self.griffin_lim_iters if iters is None else iters)
@@ -374,10 +379,11 @@ class AudioProcessor(object):
         if workspace is None:
             workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         sc = torch.empty((max(1, iters), layout.n_utts, 2), dtype=torch.float32, device=dev) if return_sc else None
-        L.check(plan.lib.ttsa_griffin_lim(plan.handle, layout.handle, self._ptr(spec_packed), int(spec_kind), iters,
-                                          self._ptr(init_angles), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
-                                          L.GL_DEEMPHASIS if deemphasis else 0, self._ptr(out), self._ptr(sc),
-                                          self._ptr(workspace), workspace.numel(), self._stream()))
+        momentum = float(getattr(self, "griffin_lim_momentum", 0.0) if momentum is None else momentum)
+        L.check(plan.lib.ttsa_griffin_lim_fast(plan.handle, layout.handle, self._ptr(spec_packed), int(spec_kind), iters,
+                                               self._ptr(init_angles), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                               L.GL_DEEMPHASIS if deemphasis else 0, momentum, self._ptr(out),
+                                               self._ptr(sc), self._ptr(workspace), workspace.numel(), self._stream()))
         if return_sc:
             sc_val = torch.sqrt(sc[:iters, :, 0] / sc[:iters, :, 1].clamp_min(1e-30))
             return out, sc_val

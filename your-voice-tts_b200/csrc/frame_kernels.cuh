@@ -46,6 +46,8 @@ struct FrameArgs {
   float* sc_acc;          // [B, 2]          GL_ITER with SC: (sum (|X|-S)^2, sum S^2)
   unsigned long long seed;
   int preemph;            // ANALYSIS: apply y[n] - p*y[n-1] while staging
+  const float* wav_prev;  // GL_ITER with momentum: the estimate before wav_in; the kernel transforms wav_in - beta * wav_prev
+  float beta;             //   beta = momentum / (1 + momentum)   (fast Griffin-Lim, opt-in; not in the reference)
   int debug;              // profiling only (TTSA_DEBUG): 1 = skip the frame phase, 2 = skip overlap-add + staging work
 };
 
@@ -151,7 +153,7 @@ __device__ __forceinline__ float2 shfl2(float a, float b, int srclane) {
 }
 
 // HOP, WIN > 0: geometry fixed at compile time (the shipped configurations); 0: read from Geo at run time.
-template <int MODE, int SRC, int NZ, bool SC, int HOP = 0, int WIN = 0>
+template <int MODE, int SRC, int NZ, bool SC, int HOP = 0, int WIN = 0, bool MOM = false>
 __global__ void __launch_bounds__(kThreads, 2)
 frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -248,6 +250,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     const long long frow0 = bd.frame_off[u];
     const long long woff = bd.wav_off[u];
     const float* __restrict__ src = (MODE != MODE_SYNTH) ? a.wav_in + woff : nullptr;
+    const float* __restrict__ srcp = MOM ? a.wav_prev + woff : nullptr;     // fast Griffin-Lim: previous estimate
 
     // frames of earlier tiles still overlap this segment's first owned sample: recompute them (no output)
     const bool warm = (MODE != MODE_ANALYSIS) && ja > 0 && ly.nwarm > 0;
@@ -269,6 +272,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
           float val = 0.0f;
           if (s < ly.span_len) {
             val = __ldg(sp + s);
+            if constexpr (MOM) val = fmaf(-a.beta, __ldg(srcp + i0 + s), val);
             if (MODE == MODE_ANALYSIS && a.preemph) val = fmaf(-g.preemph, __ldg(sp + s - 1), val);
           }
           stg[e] = val;
@@ -281,6 +285,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
           if (s < ly.span_len) {
             const int j = reflect_index(i0 + s, L);
             val = __ldg(src + j);
+            if constexpr (MOM) val = fmaf(-a.beta, __ldg(srcp + j), val);
             if (MODE == MODE_ANALYSIS && a.preemph) val = fmaf(-g.preemph, j > 0 ? __ldg(src + j - 1) : 0.0f, val);
           }
           stg[e] = val;
@@ -296,6 +301,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
       for (int s = tid + kStage * kThreads; s < ly.span_len; s += kThreads) {     // spans longer than the register window
         const int j = reflect_index(i0 + s, L);
         float val = __ldg(src + j);
+        if constexpr (MOM) val = fmaf(-a.beta, __ldg(srcp + j), val);
         if (MODE == MODE_ANALYSIS && a.preemph) val = fmaf(-g.preemph, j > 0 ? __ldg(src + j - 1) : 0.0f, val);
         ((s & 1) ? plane1 : plane0)[s >> 1] = val;
       }

@@ -10,14 +10,14 @@ extern std::atomic<unsigned long long> g_launches;
 // Opt every instantiation in to `smem_bytes` of dynamic shared memory and report the resident CTAs per SM of the
 // Griffin-Lim iteration kernel.  Returns nullptr or an error string.
 const char* configure_frame_kernels(size_t smem_bytes, int* ctas_per_sm);
-const char* launch_frame_kernel(int mode, int src, int nz, bool sc, bool fixed, int grid, size_t smem_bytes, cudaStream_t st,
+const char* launch_frame_kernel(int mode, int src, int nz, bool sc, bool fixed, bool mom, int grid, size_t smem_bytes, cudaStream_t st,
                                 const Geo& g, const Tables& tb, const BatchDev& bd, const FrameArgs& a);
 
 // per translation unit
 const char* configure_gl(size_t smem_bytes, int* ctas_per_sm);
 const char* configure_synth(size_t smem_bytes);
 const char* configure_analysis(size_t smem_bytes);
-const char* launch_gl(int src, int nz, bool sc, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
+const char* launch_gl(int src, int nz, bool sc, bool fixed, bool mom, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 const char* launch_synth(int src, int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 const char* launch_analysis(int out, int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 
@@ -56,27 +56,27 @@ inline const char* set_smem(K kernel, size_t /*smem_bytes*/) {
 // get class-20 kernels with the geometry as template constants; everything else runs the run-time-geometry kernels.
 #define TTSA_FIXED_GEOS(X) X(275, 1102) X(200, 800) X(300, 1200)
 
-template <int MODE, int SRC, bool SC>
+template <int MODE, int SRC, bool SC, bool MOM = false>
 inline const char* configure_variants(size_t smem_bytes) {
   const char* e;
-  if ((e = set_smem(frame_kernel<MODE, SRC, 20, SC>, smem_bytes))) return e;
-  if ((e = set_smem(frame_kernel<MODE, SRC, 32, SC>, smem_bytes))) return e;
-#define TTSA_X(H, W) if ((e = set_smem(frame_kernel<MODE, SRC, 20, SC, H, W>, smem_bytes))) return e;
+  if ((e = set_smem(frame_kernel<MODE, SRC, 20, SC, 0, 0, MOM>, smem_bytes))) return e;
+  if ((e = set_smem(frame_kernel<MODE, SRC, 32, SC, 0, 0, MOM>, smem_bytes))) return e;
+#define TTSA_X(H, W) if ((e = set_smem(frame_kernel<MODE, SRC, 20, SC, H, W, MOM>, smem_bytes))) return e;
   TTSA_FIXED_GEOS(TTSA_X)
 #undef TTSA_X
   return nullptr;
 }
 
-template <int MODE, int SRC, bool SC>
+template <int MODE, int SRC, bool SC, bool MOM = false>
 inline const char* launch_variant(int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo& g, const Tables& tb,
                                   const BatchDev& bd, const FrameArgs& a) {
-  if (nz != 20) TTSA_LAUNCH((frame_kernel<MODE, SRC, 32, SC>));
+  if (nz != 20) TTSA_LAUNCH((frame_kernel<MODE, SRC, 32, SC, 0, 0, MOM>));
   if (fixed) {
-#define TTSA_X(H, W) if (g.ly.hop == H && g.ly.win == W) TTSA_LAUNCH((frame_kernel<MODE, SRC, 20, SC, H, W>));
+#define TTSA_X(H, W) if (g.ly.hop == H && g.ly.win == W) TTSA_LAUNCH((frame_kernel<MODE, SRC, 20, SC, H, W, MOM>));
     TTSA_FIXED_GEOS(TTSA_X)
 #undef TTSA_X
   }
-  TTSA_LAUNCH((frame_kernel<MODE, SRC, 20, SC>));
+  TTSA_LAUNCH((frame_kernel<MODE, SRC, 20, SC, 0, 0, MOM>));
 }
 
 }  // namespace ttsa

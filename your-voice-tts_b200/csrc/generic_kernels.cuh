@@ -119,6 +119,7 @@ gen_frame_kernel(const GenGeo g, const GenTables tb, const BatchDev bd, const Fr
         if (m >= 0 && m < g.win) {
           const int j = reflect_index(t * g.hop - N / 2 + n, L);
           float x = src[j];
+          if (MODE == MODE_GL_ITER && a.wav_prev != nullptr) x = fmaf(-a.beta, a.wav_prev[woff + j], x);   // momentum mode
           if (MODE == MODE_ANALYSIS && a.preemph) x = fmaf(-g.preemph, j > 0 ? src[j - 1] : 0.0f, x);
           v = x * tb.win[m];
         }

@@ -639,12 +639,12 @@ static int check_work(const ttsa_plan* plan, const ttsa_batch* batch) {
 }
 
 static int launch_frames(const ttsa_plan* plan, const ttsa_batch* batch, int mode, int src, bool sc,
-                         const FrameArgs& args, cudaStream_t st) {
+                         const FrameArgs& args, cudaStream_t st, bool mom = false) {
   if (batch->dev.total_tiles == 0) return TTSA_OK;
   const int max_ctas = plan->ctas_per_sm * plan->num_sms;
   const int grid = batch->dev.total_tiles < max_ctas ? batch->dev.total_tiles : max_ctas;
   const size_t smem = ((size_t)plan->geo.ly.sm_total + ((mode == MODE_ANALYSIS && src == OUT_FEATURES) ? plan->geo.mel_smem_floats : 0)) * 4;
-  const char* err = launch_frame_kernel(mode, src, plan->nz, sc, plan->fixed_geo, grid, smem, st,
+  const char* err = launch_frame_kernel(mode, src, plan->nz, sc, plan->fixed_geo, mom, grid, smem, st,
                                         plan->geo, plan->tb, batch->dev, args);
   if (err) return fail(TTSA_ERR_CUDA, "frame kernel launch (mode %d): %s", mode, err);
   return TTSA_OK;
@@ -692,7 +692,7 @@ extern "C" size_t ttsa_deemphasis_workspace_bytes(const ttsa_plan* plan, const t
 extern "C" size_t ttsa_griffin_lim_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* batch) {
   if (!plan || !batch) return 0;
   const size_t wav = ((size_t)batch->total_samples * 4 + 255) / 256 * 256 + 256;
-  return 2 * wav + ttsa_deemphasis_workspace_bytes(plan, batch);
+  return 3 * wav + ttsa_deemphasis_workspace_bytes(plan, batch);     // two estimates + one more for the momentum mode
 }
 
 static int deemph_launch(const ttsa_plan* plan, const ttsa_batch* batch, const float* x, float* y, float* agg, cudaStream_t st) {
@@ -823,7 +823,16 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
                                 int iters, const float* init_angles_dev, uint64_t seed, uint32_t flags,
                                 float* wav_out_dev, float* sc_log_dev, void* workspace_dev, size_t workspace_bytes,
                                 void* stream) {
+  return ttsa_griffin_lim_fast(plan, batch, spec_dev, spec_kind, iters, init_angles_dev, seed, flags, 0.0, wav_out_dev,
+                               sc_log_dev, workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* batch, const float* spec_dev, int spec_kind,
+                                     int iters, const float* init_angles_dev, uint64_t seed, uint32_t flags, double momentum,
+                                     float* wav_out_dev, float* sc_log_dev, void* workspace_dev, size_t workspace_bytes,
+                                     void* stream) {
   if (int rc = check_work(plan, batch)) return rc;
+  if (!(momentum >= 0.0 && momentum < 1.0)) return fail(TTSA_ERR_BAD_ARG, "momentum %g outside [0, 1)", momentum);
   if (!spec_dev || !wav_out_dev || !workspace_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
   if (spec_kind != TTSA_SPEC_MAGNITUDE && spec_kind != TTSA_SPEC_NORM_DB) return fail(TTSA_ERR_BAD_ARG, "bad spec_kind %d", spec_kind);
   if (iters < 0) return fail(TTSA_ERR_BAD_ARG, "iters < 0");
@@ -835,12 +844,22 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
   const size_t wav_bytes = ((size_t)batch->total_samples * 4 + 255) / 256 * 256 + 256;
   float* wsA = (float*)workspace_dev;
   float* wsB = (float*)((char*)workspace_dev + wav_bytes);
-  float* agg = (float*)((char*)workspace_dev + 2 * wav_bytes);
-  // write k (0 = initial istft, 1..iters = iterations) goes to bufs[(k + s) & 1]; the last one must land in `last`
-  float* bufs[2];
+  float* wsC = (float*)((char*)workspace_dev + 2 * wav_bytes);
+  float* agg = (float*)((char*)workspace_dev + 3 * wav_bytes);
+  // write k (0 = initial istft, 1..iters = iterations) goes to bufs[k % nb]; the last one must land in `last`.
+  // nb = 2 (ping-pong), or 3 with momentum: iteration k reads estimates k-1 and k-2.
+  const bool mom = momentum > 0.0 && iters > 1;
+  const float beta = (float)(momentum / (1.0 + momentum));
+  const int nb = mom ? 3 : 2;
+  float* bufs[3] = {nullptr, nullptr, nullptr};
   float* last;
-  if (deemph) { bufs[0] = wsA; bufs[1] = wsB; last = (iters & 1) ? wsB : wsA; }
-  else        { bufs[iters & 1] = wav_out_dev; bufs[(iters & 1) ^ 1] = wsA; last = wav_out_dev; }
+  if (deemph) { bufs[0] = wsA; bufs[1] = wsB; bufs[2] = wsC; last = bufs[iters % nb]; }
+  else {
+    last = wav_out_dev;
+    bufs[iters % nb] = wav_out_dev;
+    float* spare[2] = {wsA, wsB};
+    for (int i = 0, k = 0; i < nb; ++i) if (bufs[i] == nullptr) bufs[i] = spare[k++];
+  }
   if (sc_log_dev && iters > 0) CUDA_TRY(cudaMemsetAsync(sc_log_dev, 0, (size_t)iters * batch->B * 2 * 4, st));
 
   if (plan->generic) {
@@ -849,11 +868,12 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
     if (int rc = gen_synthesise(plan, batch, MODE_SYNTH, spec_kind, a, st)) return rc;
     for (int i = 1; i <= iters; ++i) {
       FrameArgs b{};
-      b.spec = spec_dev; b.wav_in = bufs[(i - 1) & 1]; b.wav_out = bufs[i & 1];
+      b.spec = spec_dev; b.wav_in = bufs[(i - 1) % nb]; b.wav_out = bufs[i % nb];
+      if (mom && i >= 2) { b.wav_prev = bufs[(i - 2) % nb]; b.beta = beta; }
       b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
       if (int rc = gen_synthesise(plan, batch, MODE_GL_ITER, spec_kind, b, st)) return rc;
     }
-    if (bufs[iters & 1] != last) return fail(TTSA_ERR_CUDA, "internal: buffer rotation");
+    if (bufs[iters % nb] != last) return fail(TTSA_ERR_CUDA, "internal: buffer rotation");
     if (deemph) return deemph_launch(plan, batch, last, wav_out_dev, agg, st);
     return TTSA_OK;
   }
@@ -864,15 +884,17 @@ extern "C" int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, 
   for (int i = 1; i <= iters; ++i) {
     FrameArgs b{};
     b.spec = spec_dev; b.spec_end = spec_dev + (size_t)batch->total_frames * kF;
-    b.wav_in = bufs[(i - 1) & 1]; b.wav_out = bufs[i & 1];
+    b.wav_in = bufs[(i - 1) % nb]; b.wav_out = bufs[i % nb];
+    const bool mom_i = mom && i >= 2;                         // the first iteration has no estimate before its input
+    if (mom_i) { b.wav_prev = bufs[(i - 2) % nb]; b.beta = beta; }
     b.wav_end = b.wav_in + batch->total_samples;
     { const char* dbg = std::getenv("TTSA_DEBUG"); b.debug = dbg ? std::atoi(dbg) : 0; }
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
-    if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st)) {
+    if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st, mom_i)) {
       return rc;
     }
   }
-  if (bufs[iters & 1] != last) return fail(TTSA_ERR_CUDA, "internal: buffer rotation");
+  if (bufs[iters % nb] != last) return fail(TTSA_ERR_CUDA, "internal: buffer rotation");
   if (deemph) return deemph_launch(plan, batch, last, wav_out_dev, agg, st);
   return TTSA_OK;
 }
