@@ -652,3 +652,33 @@ def test_fast_griffin_lim_momentum_opt_in():
                                init_angles=torch.from_numpy(np.ascontiguousarray(angg.T)).to(dev), momentum=0.9)
     wgo = orcg._griffin_lim_fast(Sg, 0.9, init_angles=angg)
     assert snr_db(wgo, wg[:len(wgo)].cpu().numpy()) >= GL_SNR_DB
+
+
+def test_tacotron2_output_to_waveform_cfg4(tacotron2_postnet):
+    """BASELINE configs[3]: the postnet output of the reference's Tacotron2 (fixture produced from models/tacotron2.py)
+    stays on the device as [1, T, 80] and goes through inv_mel_spectrogram (60 iterations, config.json audio) end to
+    end; the reference's own path for the same tensor (utils/synthesis.py:53-67: .cpu().numpy(), transpose,
+    ap.inv_mel_spectrogram) is the oracle, with the initial phases injected identically."""
+    ap, orc = _ap(MAIN_AUDIO), OracleAudioProcessor(**MAIN_AUDIO)
+    mel = tacotron2_postnet                                     # [482, 80], roughly in [-0.35, 0.26]: _denormalize clips
+    assert mel.shape == (482, 80)
+    T = mel.shape[0]
+    ang = (2 * np.pi * np.random.default_rng(42).random((1025, T))).astype(np.float32)
+    wo, sco = orc.inv_mel_spectrogram(mel.T, init_angles=ang, return_sc=True)
+    dev = torch.device("cuda")
+    postnet = torch.from_numpy(mel).to(dev).unsqueeze(0)       # [1, T, 80] as models/tacotron2.py:62-73 returns it
+    ang_dev = torch.from_numpy(np.ascontiguousarray(ang.T)).to(dev)
+    wavs = ap.inv_mel_spectrogram_padded(postnet, [T], init_angles=ang_dev)
+    w = wavs[0].cpu().numpy()
+    assert w.shape == wo.shape == (275 * (T - 1),)
+    assert snr_db(wo, w) >= GL_SNR_DB, snr_db(wo, w)
+    w2, sc = ap.inv_mel_spectrogram(mel.T, init_angles=ang, return_sc=True)      # the drop-in numpy call
+    assert snr_db(wo, w2) >= GL_SNR_DB
+    np.testing.assert_allclose(sc, sco, rtol=SC_RTOL)
+    # and straight to a WAV file as the server does (one sentence)
+    data = ap.sentences_to_wav_bytes([postnet[0]], init_angles=ang_dev)
+    import io
+    from scipy.io import wavfile
+    sr, pcm = wavfile.read(io.BytesIO(data))
+    want = orc.save_wav_int16(orc.server_concat([wo]))
+    assert sr == 22050 and len(pcm) == len(want) and np.abs(pcm.astype(int) - want.astype(int)).max() <= 2

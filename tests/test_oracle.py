@@ -166,3 +166,13 @@ def test_save_wav_int16_matches_reference_formula_and_scipy_container(tmp_path):
     ref = io.BytesIO()
     wavfile.write(ref, MAIN_AUDIO["sample_rate"], pcm)
     assert ap.wav_file_bytes(pcm) == ref.getvalue()
+
+
+def test_tacotron2_fixture_shape_and_range(tacotron2_postnet):
+    """The configs[3] fixture is what SURVEY section 8d predicts for the random-init reference model: 2 N + 22 = 482
+    frames for N = 230 tokens, 80 mels, values around zero that _denormalize clips into [0, 1]."""
+    mel = tacotron2_postnet
+    assert mel.shape == (482, 80) and mel.dtype == np.float32 and np.isfinite(mel).all()
+    orc = OracleAudioProcessor(**MAIN_AUDIO)
+    d = orc._denormalize(mel.astype(np.float64))
+    assert d.min() >= orc.min_level_db - 1e-9 and d.max() <= 0.0 + 1e-9

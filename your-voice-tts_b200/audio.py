@@ -465,7 +465,6 @@ class AudioProcessor(object):
                                              seed=seed)
         return lay.split_wav(out)
 
-    # ------------------------------------------------------------------------------------------ reference API
     # ------------------------------------------------------------------------------------------ waveform post-processing
     def wav_peaks_batch(self, wav_packed, layout, lens=None):
         """max |wav_u| per utterance: the peak save_wav normalises by (utils/audio.py:57).  -> [B] float32"""
