@@ -682,3 +682,27 @@ def test_tacotron2_output_to_waveform_cfg4(tacotron2_postnet):
     sr, pcm = wavfile.read(io.BytesIO(data))
     want = orc.save_wav_int16(orc.server_concat([wo]))
     assert sr == 22050 and len(pcm) == len(want) and np.abs(pcm.astype(int) - want.astype(int)).max() <= 2
+
+
+def test_mel_gemm_variants_agree(monkeypatch):
+    """mel <-> linear: the pipelined tcgen05 kernel (default), the un-pipelined tensor-core kernel (TTSA_MEL_GEMM=tc_simple)
+    and the fp32 SIMT kernels (TTSA_MEL_GEMM=simt) all meet the float64 product within the same bound."""
+    from your_voice_tts_b200 import audio as A
+    orc = OracleAudioProcessor(**MAIN_AUDIO)
+    rng = np.random.default_rng(12)
+    T = 300
+    mel_amp = (rng.random((80, T)) ** 3).astype(np.float32) * 5.0
+    lin_amp = (rng.random((1025, T)) ** 3).astype(np.float32) * 5.0
+    want_lin = np.maximum(1e-10, np.linalg.pinv(orc._build_mel_basis()) @ mel_amp.astype(np.float64))
+    want_mel = orc._build_mel_basis() @ lin_amp.astype(np.float64)
+    for mode in ("", "tc_simple", "simt"):
+        if mode:
+            monkeypatch.setenv("TTSA_MEL_GEMM", mode)
+        A._PLAN_CACHE.clear()
+        ap = _ap(MAIN_AUDIO)
+        got_lin = ap._mel_to_linear(mel_amp)
+        got_mel = ap._linear_to_mel(lin_amp)
+        assert np.abs(got_lin - want_lin).max() <= 3e-6 * np.abs(want_lin).max(), (mode, np.abs(got_lin - want_lin).max() / np.abs(want_lin).max())
+        assert np.abs(got_mel - want_mel).max() <= 3e-6 * np.abs(want_mel).max(), (mode, np.abs(got_mel - want_mel).max() / np.abs(want_mel).max())
+    monkeypatch.delenv("TTSA_MEL_GEMM")
+    A._PLAN_CACHE.clear()

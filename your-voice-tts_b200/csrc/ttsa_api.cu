@@ -64,6 +64,8 @@ struct ttsa_plan {
   std::vector<double> h_inv_mel;   // [F][num_mels]
   int nz = 32;                     // compile-time zero-pruning class of the frame kernels (20 or 32)
   int ctas_per_sm = 1;
+  int debug = 0;                   // TTSA_DEBUG (profiling: skip phases of the iteration kernel), read once per plan
+  int mel_gemm = 0;                // TTSA_MEL_GEMM: 0 default (tensor cores), 1 "simt", 2 "tc_simple"
   bool generic = false;            // n_fft != 2048: the any-size kernels of generic_kernels.cuh
   GenGeo gg;
   GenTables gt;
@@ -482,6 +484,9 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
   p->ctas_per_sm = occ < 1 ? 1 : occ;
   { const char* gen = std::getenv("TTSA_GENERIC_GEO"); p->fixed_geo = !(gen != nullptr && std::atoi(gen) != 0); }
+  { const char* dbg = std::getenv("TTSA_DEBUG"); p->debug = dbg ? std::atoi(dbg) : 0; }
+  { const char* mg = std::getenv("TTSA_MEL_GEMM");
+    p->mel_gemm = mg == nullptr ? 0 : (std::strcmp(mg, "simt") == 0 ? 1 : (std::strcmp(mg, "tc_simple") == 0 ? 2 : 0)); }
   cudaError_t e = cudaFuncSetAttribute(mel_to_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMtlMaxK * (kMtlBins + kMtlRows) * 4);
   if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "mel kernel configuration: %s", cudaGetErrorString(e)); }
@@ -888,7 +893,7 @@ extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* ba
     const bool mom_i = mom && i >= 2;                         // the first iteration has no estimate before its input
     if (mom_i) { b.wav_prev = bufs[(i - 2) % nb]; b.beta = beta; }
     b.wav_end = b.wav_in + batch->total_samples;
-    { const char* dbg = std::getenv("TTSA_DEBUG"); b.debug = dbg ? std::atoi(dbg) : 0; }
+    b.debug = plan->debug;
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
     if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st, mom_i)) {
       return rc;
@@ -908,12 +913,11 @@ extern "C" int ttsa_mel_to_linear(const ttsa_plan* plan, const ttsa_batch* batch
   DeviceGuard guard(plan->device);
   MelParams mp = plan->mel;
   mp.rows = batch->total_frames;
-  const char* simt = std::getenv("TTSA_MEL_GEMM");
-  if (plan->generic || (simt != nullptr && std::strcmp(simt, "simt") == 0)) {   // fp32 SIMT kernel (any num_freq; profiling / cross-check)
+  if (plan->generic || plan->mel_gemm == 1) {   // fp32 SIMT kernel (any num_freq; profiling / cross-check)
     dim3 grid((mp.F + kMtlBins - 1) / kMtlBins, (unsigned)((batch->total_frames + kMtlRows - 1) / kMtlRows));
     const size_t smem = (size_t)mp.num_mels * (kMtlBins + kMtlRows) * 4;
     mel_to_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mp, plan->d_pinvT, plan->ldp, mel_dev, lin_out_dev, in_kind, out_kind);
-  } else if (plan->d_pinv_tc96 != nullptr && !(simt != nullptr && std::strcmp(simt, "tc_simple") == 0)) {
+  } else if (plan->d_pinv_tc96 != nullptr && plan->mel_gemm != 2) {
     // pipelined tensor-core kernel: one CTA per 128-frame tile walks all bin tiles
     TcGemmParams tp;
     tp.mp = mp; tp.a = mel_dev; tp.lda = mp.num_mels; tp.k_total = mp.num_mels; tp.n_chunks = 1;
@@ -945,11 +949,10 @@ extern "C" int ttsa_linear_to_mel(const ttsa_plan* plan, const ttsa_batch* batch
   DeviceGuard guard(plan->device);
   MelParams mp = plan->mel;
   mp.rows = batch->total_frames;
-  const char* simt = std::getenv("TTSA_MEL_GEMM");
   if (plan->generic) {
     const unsigned grid = (unsigned)((batch->total_frames + 7) / 8);
     gen_linear_to_mel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp, mp.F, plan->gt, lin_dev, mel_out_dev, in_kind, out_kind);
-  } else if (plan->d_mel_tc == nullptr || (simt != nullptr && std::strcmp(simt, "simt") == 0)) {   // banded fp32 SIMT kernel
+  } else if (plan->d_mel_tc == nullptr || plan->mel_gemm == 1) {   // banded fp32 SIMT kernel
     const unsigned grid = (unsigned)((batch->total_frames + 7) / 8);
     linear_to_mel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp, plan->tb, lin_dev, mel_out_dev, in_kind, out_kind);
   } else {
