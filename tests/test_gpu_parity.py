@@ -706,3 +706,19 @@ def test_mel_gemm_variants_agree(monkeypatch):
         assert np.abs(got_mel - want_mel).max() <= 3e-6 * np.abs(want_mel).max(), (mode, np.abs(got_mel - want_mel).max() / np.abs(want_mel).max())
     monkeypatch.delenv("TTSA_MEL_GEMM")
     A._PLAN_CACHE.clear()
+
+
+def test_mel_basis_that_does_not_fit_shared_memory():
+    """mel_fmax=None (filters up to sr/2: 2 050 taps) does not fit beside the frame buffers, so the feature kernel
+    reads the banded basis from global memory; 128 mels likewise.  Same forward bar."""
+    for audio in (dict(MAIN_AUDIO, mel_fmax=None), dict(MAIN_AUDIO, num_mels=128, mel_fmax=11000.0)):
+        ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+        y = synth_speech_like(17, n_samples=275 * 50 + 100)
+        mel, mel_o = ap.melspectrogram(y), orc.melspectrogram(y)
+        assert mel.shape == mel_o.shape
+        assert np.mean(np.abs(mel - mel_o) <= FWD_TOL) >= 0.995
+        ang = (2 * np.pi * np.random.default_rng(3).random((1025, mel_o.shape[1]))).astype(np.float32)
+        a2 = dict(audio, griffin_lim_iters=4)
+        w = _ap(a2).inv_mel_spectrogram(mel_o.astype(np.float32), init_angles=ang)
+        wo = OracleAudioProcessor(**a2).inv_mel_spectrogram(mel_o.astype(np.float32), init_angles=ang)
+        assert snr_db(wo, w) >= GL_SNR_DB, snr_db(wo, w)
