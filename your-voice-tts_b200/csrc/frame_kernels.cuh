@@ -781,8 +781,13 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               if (fa >= fv_lo && fa < fv_hi) va = fmaf(smem[fa * kBufFloats + po], w, va);
               if (fb >= fv_lo && fb < fv_hi) vb = fmaf(smem[fb * kBufFloats + po], w, vb);
             }
-            emit(jl, rr, sa, va);
-            if (jl < ND - 1) emit(jl + kNF, rr, sb, vb);
+            if (interior) {   // owned, inside the signal, every overlapping frame exists: no edge handling
+              dst[i0 + sa] = va * pw[rr];
+              if (jl < ND - 1 && sb < ly.span_len) carry[sb - kNF * ly.hop] = vb;
+            } else {
+              emit(jl, rr, sa, va);
+              if (jl < ND - 1) emit(jl + kNF, rr, sb, vb);
+            }
           }
         }
         has_carry = true;
