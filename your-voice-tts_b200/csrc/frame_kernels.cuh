@@ -21,6 +21,11 @@
 // All per-frame arithmetic runs on packed fp32 pairs (FFMA2/FADD2/FMUL2, fft32p.cuh): a thread's 32 complex values are
 // 16 (re, re) + 16 (im, im) register pairs.  The FP32 lane work is unchanged, but the packed form halves the issue
 // slots it needs, and the kernel is issue-bound (measured: FP pipe 39 % busy at 64 % issue utilisation before packing).
+//
+// Template parameters HOP / WIN fix the geometry at compile time for the shipped configurations (every shared-memory
+// offset and bound becomes an immediate; Layout in common.cuh is shared with the host); MOM adds the previous estimate
+// for the opt-in fast Griffin-Lim.  The kernel sits at its 128-register limit (2 CTAs x 8 warps per SM): DESIGN.md
+// section 4 lists the reorderings and extra live values that were measured and cost 1-4 % each.
 #pragma once
 #include "common.cuh"
 #include "fft32p.cuh"
