@@ -722,3 +722,21 @@ def test_mel_basis_that_does_not_fit_shared_memory():
         w = _ap(a2).inv_mel_spectrogram(mel_o.astype(np.float32), init_angles=ang)
         wo = OracleAudioProcessor(**a2).inv_mel_spectrogram(mel_o.astype(np.float32), init_angles=ang)
         assert snr_db(wo, w) >= GL_SNR_DB, snr_db(wo, w)
+
+
+def test_silent_and_tiny_spectrograms_stay_finite():
+    """All-zero magnitudes give an all-zero waveform (np.angle(0) = 0 path), magnitudes far below float32's useful
+    range stay finite, and a quiet-but-real signal (-120 dB) still meets the bar: the select-free zero-phase offset
+    (1e-18) only matters for frames whose whole spectrum lies below ~1e-13."""
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=5)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    T = 37
+    ang = (2 * np.pi * np.random.default_rng(0).random((1025, T))).astype(np.float32)
+    w = ap._griffin_lim(np.zeros((1025, T), dtype=np.float32), init_angles=ang)
+    assert w.shape == (275 * (T - 1),) and np.all(w == 0.0)
+    w = ap._griffin_lim(np.full((1025, T), 1e-25, dtype=np.float32), init_angles=ang)
+    assert np.isfinite(w).all() and np.abs(w).max() < 1e-20
+    y = synth_speech_like(3, n_samples=275 * (T - 1) + 50) * 1e-6
+    S = np.abs(lr_stft(y.astype(np.float64), 2048, 275, 1102)).astype(np.float32)
+    wq, wqo = ap._griffin_lim(S, init_angles=ang), orc._griffin_lim(S, init_angles=ang)
+    assert snr_db(wqo, wq) >= GL_SNR_DB, snr_db(wqo, wq)

@@ -423,7 +423,8 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
                 const float2 XpI = __ffma2_rn(E2I, splat(-2.0f), XkI);
                 // Y = S X/|X| with np.angle(0) = 0, i.e. Y = S where X == 0: a real offset far below the rounding
                 // error of any computed bin (2X is O(1e-7 * frame peak) at best) gives exact zeros the phase 0 without
-                // a select, and the floor inside |2X|^2 keeps the reciprocal square root finite.
+                // a select, and the floor inside |2X|^2 keeps the reciprocal square root finite.  (Only a frame whose
+                // WHOLE spectrum lies below ~1e-13, i.e. -260 dB, would see its phases biased by the offset.)
                 XkR = __fadd2_rn(XkR, splat(kPhaseEps));
                 XpR = __fadd2_rn(XpR, splat(kPhaseEps));
                 const float2 mk = __ffma2_rn(XkI, XkI, __ffma2_rn(XkR, XkR, splat(kTiny)));
