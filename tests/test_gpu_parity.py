@@ -740,3 +740,25 @@ def test_silent_and_tiny_spectrograms_stay_finite():
     S = np.abs(lr_stft(y.astype(np.float64), 2048, 275, 1102)).astype(np.float32)
     wq, wqo = ap._griffin_lim(S, init_angles=ang), orc._griffin_lim(S, init_angles=ang)
     assert snr_db(wqo, wq) >= GL_SNR_DB, snr_db(wqo, wq)
+
+
+def test_device_phases_opt_in_for_the_numpy_api():
+    """AudioProcessor(device_phases=True): the drop-in numpy calls draw their initial phases on the device (seeded from
+    numpy's global RNG, so np.random.seed still repeats a run) instead of uploading 2*pi*np.random.rand(F, T)."""
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=30)
+    ap, ap_d, orc = _ap(audio), _ap(dict(audio, device_phases=True)), OracleAudioProcessor(**audio)
+    assert ap.device_phases is False and ap_d.device_phases is True
+    y = synth_speech_like(9, n_samples=275 * 80)
+    spec = orc.spectrogram(y).astype(np.float32)
+    np.random.seed(5); w1 = ap_d.inv_spectrogram(spec)
+    np.random.seed(5); w2 = ap_d.inv_spectrogram(spec)
+    np.random.seed(6); w3 = ap_d.inv_spectrogram(spec)
+    assert np.array_equal(w1, w2) and not np.array_equal(w1, w3)
+    # same quality as with host-drawn phases: spectral error of the result against the target magnitudes
+    S = orc._db_to_amp(orc._denormalize(spec.astype(np.float64)) + orc.ref_level_db) ** orc.power
+    def err(w):
+        x = orc.apply_preemphasis(np.asarray(w, dtype=np.float64))      # undo the de-emphasis of inv_spectrogram
+        return np.linalg.norm(np.abs(lr_stft(x, 2048, 275, 1102)) - S) / np.linalg.norm(S)
+    np.random.seed(7)
+    e_host, e_dev = err(ap.inv_spectrogram(spec)), err(w1)
+    assert abs(e_dev - e_host) <= 0.15 * e_host, (e_dev, e_host)

@@ -226,6 +226,10 @@ class AudioProcessor(object):
         # extension (not a reference field, so it is set after the member print-out): > 0 switches every inversion to
         # fast Griffin-Lim with that momentum; 0 keeps the reference's algorithm
         self.griffin_lim_momentum = float(kwargs.get("griffin_lim_momentum", 0.0))
+        # extension: True = initial Griffin-Lim phases from the device RNG when none are injected (the reference draws
+        # 2*pi*np.random.rand(F, T) on the host, utils/audio.py:183, which dominates the latency of a single call)
+        self.device_phases = bool(kwargs.get("device_phases", False))
+        self._phase_seed = 0
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _stft_parameters(self):
@@ -655,6 +659,11 @@ class AudioProcessor(object):
         reproduced: 2*pi*np.random.rand(*S.shape) on the [D, T] array (utils/audio.py:183), consuming numpy's
         global RNG exactly as the reference does."""
         if init_angles is None:
+            if self.device_phases:
+                # opt-in: let the kernel draw the phases (counter RNG keyed by a seed taken from numpy's global RNG, so
+                # np.random.seed still makes runs repeatable) instead of generating and uploading F x T floats
+                self._phase_seed = int(np.random.randint(0, 2 ** 31 - 1))
+                return None
             init_angles = 2.0 * np.pi * np.random.rand(*shape_dt)
         a = self._to_dev(np.asarray(init_angles, dtype=np.float32) if not self._is_tensor(init_angles) else init_angles)
         return self._transpose(a)
@@ -663,7 +672,7 @@ class AudioProcessor(object):
         """utils/audio.py:154-162; normalised [num_freq, T] -> waveform [hop*(T-1)]"""
         tt, lay = self._dt_in(spectrogram)
         ang = self._host_angles(tuple(tt.shape[::-1]), init_angles)
-        out = self.inv_spectrogram_batch(tt, lay, init_angles=ang, return_sc=return_sc)
+        out = self.inv_spectrogram_batch(tt, lay, init_angles=ang, seed=self._phase_seed, return_sc=return_sc)
         if return_sc:
             return self._ret(out[0][:lay.wav_len[0]], spectrogram), self._ret(out[1][:, 0], spectrogram)
         return self._ret(out[:lay.wav_len[0]], spectrogram)
@@ -672,7 +681,7 @@ class AudioProcessor(object):
         """utils/audio.py:164-172; normalised [num_mels, T] -> waveform [hop*(T-1)]"""
         tt, lay = self._dt_in(mel_spectrogram)
         ang = self._host_angles((self.num_freq, tt.shape[0]), init_angles)
-        out = self.inv_mel_spectrogram_batch(tt, lay, init_angles=ang, return_sc=return_sc)
+        out = self.inv_mel_spectrogram_batch(tt, lay, init_angles=ang, seed=self._phase_seed, return_sc=return_sc)
         if return_sc:
             return self._ret(out[0][:lay.wav_len[0]], mel_spectrogram), self._ret(out[1][:, 0], mel_spectrogram)
         return self._ret(out[:lay.wav_len[0]], mel_spectrogram)
@@ -687,7 +696,7 @@ class AudioProcessor(object):
         """utils/audio.py:182-189; magnitude [num_freq, T] -> waveform"""
         tt, lay = self._dt_in(S)
         ang = self._host_angles(tuple(tt.shape[::-1]), init_angles)
-        out = self.griffin_lim_batch(tt, lay, L.SPEC_MAGNITUDE, init_angles=ang, return_sc=return_sc)
+        out = self.griffin_lim_batch(tt, lay, L.SPEC_MAGNITUDE, init_angles=ang, seed=self._phase_seed, return_sc=return_sc)
         if return_sc:
             return self._ret(out[0][:lay.wav_len[0]], S), self._ret(out[1][:, 0], S)
         return self._ret(out[:lay.wav_len[0]], S)
