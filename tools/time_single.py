@@ -17,6 +17,15 @@ for _ in range(n):
     w = ap.inv_spectrogram(spec)
 dt = (time.perf_counter() - t0) / n
 print("numpy in / numpy out: %.3f ms per call (%.0f x real time)" % (dt * 1e3, 6.0 / dt))
+apd = AudioProcessor(verbose=False, **dict(MAIN_AUDIO, device_phases=True))
+for _ in range(3):
+    w = apd.inv_spectrogram(spec)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(n):
+    w = apd.inv_spectrogram(spec)
+dtd = (time.perf_counter() - t0) / n
+print("numpy in / numpy out, device_phases=True: %.3f ms per call" % (dtd * 1e3))
 lay = ap.layout(n_frames=[482])
 st = torch.from_numpy(np.ascontiguousarray(spec.T)).cuda()
 out = ap.inv_spectrogram_batch(st, lay)
