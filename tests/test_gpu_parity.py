@@ -762,3 +762,56 @@ def test_device_phases_opt_in_for_the_numpy_api():
     np.random.seed(7)
     e_host, e_dev = err(ap.inv_spectrogram(spec)), err(w1)
     assert abs(e_dev - e_host) <= 0.15 * e_host, (e_dev, e_host)
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_randomised_configs_vs_oracle(seed):
+    """Seeded random audio blocks (sample rate, frame shift / length, normalisation flags, power, pre-emphasis, mel
+    range, ragged frame counts incl. utterance edges): forward features, stft/istft and 3 Griffin-Lim iterations with
+    injected phases against the oracle -- exercises both kernel classes, compile-time and run-time geometries and the
+    any-size path on configurations nobody hand-picked."""
+    rng = np.random.default_rng(1000 + seed)
+    sr = int(rng.choice([16000, 22050, 24000, 20000, 11025]))
+    num_freq = int(rng.choice([1025, 1025, 1025, 513, 2049]))
+    n_fft = (num_freq - 1) * 2
+    shift = float(rng.choice([5.0, 10.0, 12.5, 15.0]))
+    hop = int(shift / 1000.0 * sr)
+    ratio = float(rng.choice([2.0, 3.0, 4.0, 4.5, 6.5]))
+    win = min(n_fft, int(ratio * hop))
+    length = 1000.0 * (win + 0.5) / sr
+    audio = dict(MAIN_AUDIO, sample_rate=sr, num_freq=num_freq, frame_shift_ms=shift, frame_length_ms=length,
+                 symmetric_norm=bool(rng.integers(2)), max_norm=float(rng.choice([1.0, 4.0])),
+                 clip_norm=bool(rng.integers(2)), power=float(rng.choice([1.0, 1.2, 1.5])),
+                 preemphasis=float(rng.choice([0.0, 0.9, 0.97, 0.98])), ref_level_db=float(rng.choice([0.0, 20.0])),
+                 mel_fmin=float(rng.choice([0.0, 50.0, 95.0])), mel_fmax=float(rng.choice([3800.0, 5000.0, sr / 2.0 - 12.5])),
+                 griffin_lim_iters=3)
+    orc = OracleAudioProcessor(**audio)
+    assert (orc.hop_length, orc.win_length) == (hop, win), (orc.hop_length, orc.win_length, hop, win)
+    if win - hop > 8 * hop:
+        pytest.skip("win > 9 hop is outside the frame kernels' range")
+    ap = _ap(audio)
+    n = hop * int(rng.integers(3, 70)) + int(rng.integers(0, hop))
+    y = synth_speech_like(seed, n_samples=n, sr=sr)
+    spec, spec_o = ap.spectrogram(y), orc.spectrogram(y)
+    mel, mel_o = ap.melspectrogram(y), orc.melspectrogram(y)
+    tol = FWD_TOL * audio["max_norm"] * (2.0 if audio["symmetric_norm"] else 1.0)
+    assert spec.shape == spec_o.shape and np.mean(np.abs(spec - spec_o) <= tol) >= 0.99, (audio, np.mean(np.abs(spec - spec_o) <= tol))
+    assert mel.shape == mel_o.shape and np.mean(np.abs(mel - mel_o) <= tol) >= 0.99
+    Do = lr_stft(y.astype(np.float64), orc.n_fft, hop, win)
+    assert np.abs(ap._stft(y) - Do).max() <= 3e-6 * np.abs(Do).max()
+    # ragged Griffin-Lim batch from random magnitudes (T = 1 gives an empty waveform)
+    Ts = [int(t) for t in rng.integers(1, 45, size=4)]
+    mags = [rng.random((T, num_freq)).astype(np.float32) ** 2 for T in Ts]
+    angs = [(2 * np.pi * rng.random((T, num_freq))).astype(np.float32) for T in Ts]
+    lay = ap.layout(n_frames=Ts)
+    dev = torch.device("cuda")
+    out, sc = ap.griffin_lim_batch(torch.from_numpy(np.concatenate(mags)).to(dev), lay, L.SPEC_MAGNITUDE,
+                                   init_angles=torch.from_numpy(np.concatenate(angs)).to(dev), return_sc=True)
+    for u, T in enumerate(Ts):
+        w = lay.split_wav(out)[u].cpu().numpy()
+        assert w.shape == (hop * max(0, T - 1),)
+        if T < 2:
+            continue
+        wo, sco = orc._griffin_lim(mags[u].T, init_angles=angs[u].T, return_sc=True)
+        assert snr_db(wo, w) >= GL_SNR_DB, (audio, T, snr_db(wo, w))
+        np.testing.assert_allclose(sc[:, u].cpu().numpy(), sco, rtol=SC_RTOL)
