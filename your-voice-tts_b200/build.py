@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libttsa_b200.so")
-SOURCES = ["ttsa_api.cu", "frame_gl.cu", "frame_gl_mom.cu", "frame_synth.cu", "frame_analysis.cu"]
+SOURCES = ["ttsa_api.cu", "gl_stream.cu", "frame_gl.cu", "frame_gl_mom.cu", "frame_synth.cu", "frame_analysis.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-Xcudafe", "--diag_suppress=940"]

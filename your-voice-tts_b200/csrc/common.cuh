@@ -82,6 +82,7 @@ struct Tables {
   const float* wE;       // [1024]    w[2q]   (zero padded)
   const float* wO;       // [1024]    w[2q+1]
   const float* pw;       // [hop]    1 / sum_q w[r + q*hop]^2   (interior window-sum-square, periodic in hop)
+  const float2* pw2;     // [hop]    (pw[r], pw[(r + 1) % hop]) / n_fft   (sample pairs of the warp-stream Griffin-Lim kernel)
   const float* smem_image;  // [Layout::image_floats]  wE2 | wO2 | pw / n_fft | signed synthesis window | tw4 | g4, laid out
                             // exactly as the kernels keep them in shared memory (one bulk copy per CTA)
   // sparse mel basis (CSR over mel rows; each row is one contiguous run of bins)
@@ -102,6 +103,12 @@ struct BatchDev {
   const int* tile_off;       // [B+1] prefix sum of ceil(T/kNF)
   int B;
   int total_tiles;
+};
+
+// Work partition of the warp-stream Griffin-Lim kernel (gl_stream.cuh), built by the host with the batch.
+struct WpsDev {
+  const int* cut;     // [grid * 16 + 1] flattened frame index where each warp's range starts (non-decreasing)
+  const int* tsum;    // [B + 1] prefix sum of the frame counts (flattened frame index of each utterance's frame 0)
 };
 
 __device__ __forceinline__ int reflect_index(int i, int L) {

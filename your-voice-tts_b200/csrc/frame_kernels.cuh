@@ -110,6 +110,23 @@ __device__ __forceinline__ int span_to_smem_async(float* dst, const float* ptr, 
   }
   return off;
 }
+// The same for a compile-time length: the chunk loop is fully unrolled (one predicated LDGSTS per 32 chunks).
+template <int N>
+__device__ __forceinline__ int span_to_smem_async_n(float* dst, const float* ptr, const float* lo, const float* hi, int lane) {
+  const int off = (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ull);
+  const float* base = ptr - off;
+  const int nchunks = (off + N + 3) >> 2;
+  constexpr int kMaxChunks = (3 + N + 3) >> 2;
+  if (base >= lo && base + 4 * kMaxChunks <= hi) {
+    const float* g = base + 4 * lane;
+    float* d = dst + 4 * lane;
+#pragma unroll
+    for (int k = 0; k < (kMaxChunks + 31) / 32; ++k)
+      if (32 * k + 31 < (N >> 2) || lane + 32 * k < nchunks) cp_async16(d + 128 * k, g + 128 * k);
+    return off;
+  }
+  return span_to_smem_async(dst, ptr, N, lo, hi, lane);
+}
 // one spectrogram row (kF floats)
 __device__ __forceinline__ int row_to_smem_async(float* dst, const float* row_ptr, const float* lo, const float* hi, int lane) {
   return span_to_smem_async(dst, row_ptr, kF, lo, hi, lane);

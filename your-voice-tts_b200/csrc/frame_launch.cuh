@@ -21,6 +21,12 @@ const char* launch_gl(int src, int nz, bool sc, bool fixed, bool mom, int grid, 
 const char* launch_synth(int src, int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 const char* launch_analysis(int out, int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 
+// warp-stream Griffin-Lim iteration kernel (gl_stream.cu)
+bool gl_stream_supported(int hop, int win);
+const char* configure_gl_stream();
+const char* launch_gl_stream(int src, bool sc, int hop, int win, int grid, cudaStream_t st, const Geo&, const Tables&, const BatchDev&,
+                             const WpsDev&, const FrameArgs&);
+
 template <class K>
 inline const char* set_smem(K kernel, size_t /*smem_bytes*/) {
   // The attribute belongs to the function, not to a plan: opt in to the device maximum (227 KB on sm_100) once, so that

@@ -1,0 +1,482 @@
+// Griffin-Lim iteration, "warp stream" form (utils/audio.py:186-188): every warp owns a private run of CONSECUTIVE
+// frames of one utterance and carries the overlap-add of its run in a private shared-memory ring, so the steady state
+// has no CTA-wide barrier, no shared staging buffer and no separate overlap-add phase:
+//
+//   per frame (one warp):  cp.async'ed input span -> window -> FFT (32 x 32, one exchange) -> |S| e^{j angle X}
+//                          -> inverse FFT (same code, conjugate trick) -> window, add into the ring
+//                          -> the hop samples no later frame touches leave the ring: * 1/(N wss) -> global
+//
+// The 16 warps of the one CTA per SM drift apart and sit in different phases (FP32-bound transform passes,
+// shared-memory-bound exchanges, latency-bound per-bin step), which is what keeps the pipes busy; frame_kernel<GL_ITER>
+// (frame_kernels.cuh) runs its 8 warps in lock step between two CTA barriers per tile and spends 25 % of its warp
+// time in the overlap-add / staging / barrier phases this kernel does not have.
+//
+// Alignment.  A frame starts at sample t*hop - win/2 of its utterance, which is odd for every other frame when the hop
+// is odd (275).  All shared and global accesses here are 8-byte (sample pair) accesses on EVEN absolute sample
+// positions: an odd frame is processed as the frame that starts one sample earlier with the window shifted by one tap
+// (w'[0] = 0).  A shift of the whole frame is a phase ramp, which the per-bin projection S X/|X| and the inverse
+// transform undo exactly (the same argument as the window-relative coordinates of frame_kernels.cuh).
+//
+// Run boundaries.  The host cuts the flattened frame list into one contiguous range per warp (ttsa_batch, wps_cut).
+// A range that starts in the middle of an utterance lacks the contributions of the `kWarm` frames before it:
+//   * first warp of a CTA: those frames are recomputed (no output), as frame_kernel does per CTA segment;
+//   * any other warp: its first win - hop samples are stored as RAW partial sums; the previous warp of the same CTA
+//     keeps the matching partial sums in its ring, and after one CTA barrier at the very end the zone is finished
+//     (sum, * 1/(N wss)) -- every output sample is still written by a fixed thread in a fixed order: deterministic.
+#pragma once
+#include "frame_kernels.cuh"
+
+namespace ttsa {
+
+constexpr int kWpsWarps = 16;
+constexpr int kWpsThreads = kWpsWarps * 32;
+
+__device__ __forceinline__ float2 ld_volatile_f2(const float* p) {
+  float2 v;
+  asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+template <int HOP, int WIN>
+struct WpsGeo {
+  static_assert(WIN % 2 == 0 && HOP >= 2 && WIN >= HOP, "even window not shorter than the hop");
+  static constexpr int kOdd = HOP & 1;
+  static constexpr int kNP = WIN / 2 + kOdd;           // sample pairs of an (aligned) frame
+  static constexpr int kRows = (kNP + 31) / 32;        // rows of 32 pairs
+  static constexpr int kMH = (kRows + 1) / 2;          // packed register pairs that carry data
+  static constexpr int kRH = 32 * kRows;               // ring length in pairs
+  static constexpr int kWarm = (WIN - 1) / HOP;        // frames before t that overlap frame t's first sample
+  static constexpr int kZone = WIN - HOP;              // samples of a run's first frames that earlier frames also add to
+  static constexpr int kEmitIters = ((HOP + 1) / 2 + 31) / 32;
+  static constexpr int kFlushIters = (kNP + 31) / 32;
+  static_assert(kRows <= 20, "window too long for this kernel");
+  // shared memory (floats)
+  static constexpr int kWarpFloats = kBufFloats + 2 * kRH;
+  static constexpr int sm_tw = kWpsWarps * kWarpFloats;          // float4[16][32]
+  static constexpr int sm_g = sm_tw + 2048;                      // float4[8][32]
+  static constexpr int sm_wE = sm_g + 1024;                      // [kRH]      w[2q]
+  static constexpr int sm_wO1 = sm_wE + kRH;                     // [kRH + 4]  w[2(q-1)+1], entry 0 = 0
+  static constexpr int sm_pw = sm_wO1 + kRH + 4;                 // [HOP + 1]  1 / (n_fft wss), entry HOP = entry 0
+  static constexpr int sm_meta = sm_pw + (HOP + 4) / 4 * 4;      // int[kWpsWarps]: "head zone stored" flag per warp
+  static constexpr int sm_total = sm_meta + kWpsWarps;
+};
+
+template <int SRC, bool SC, int HOP, int WIN>
+__global__ void __launch_bounds__(kWpsThreads, 1)
+gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev wp, const FrameArgs a) {
+  using G = WpsGeo<HOP, WIN>;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr float kInvN = 1.0f / (float)kNfft;
+  constexpr float kTiny = 1e-37f;
+  constexpr float kPhaseEps = 1e-18f;
+
+  float* const buf = smem + warp * G::kWarpFloats;                 // exchange buffer / |S| row / input span landing zone
+  float2* const ring = reinterpret_cast<float2*>(buf + kBufFloats);
+  const float4* const tw4 = reinterpret_cast<const float4*>(smem + G::sm_tw);
+  const float4* const g4 = reinterpret_cast<const float4*>(smem + G::sm_g);
+  const float* const wE = smem + G::sm_wE;
+  const float* const wO1 = smem + G::sm_wO1;
+  const float* const pwn = smem + G::sm_pw;
+  volatile int* const meta = reinterpret_cast<volatile int*>(smem + G::sm_meta);
+
+  // 1 / (n_fft * window sum of squares) at sample i of an utterance with T frames, over the frames that exist
+  // (librosa: divide only where wss > tiny); the interior uses the periodic table pwn instead
+  auto inv_wss = [&](int i, int T) {
+    float ws = 0.0f;
+    const int tq = (i + WIN / 2) / HOP;                            // last frame whose window starts at or before i
+    for (int tt = tq; tt >= 0 && tt > tq - (G::kWarm + 1); --tt) {
+      const int mtap = i - (tt * HOP - WIN / 2);
+      if (tt < T && mtap >= 0 && mtap < WIN) {
+        const float wv = (mtap & 1) ? wO1[(mtap >> 1) + 1] : wE[mtap >> 1];
+        ws = fmaf(wv, wv, ws);
+      }
+    }
+    return ws > 1.17549435e-38f ? kInvN / ws : kInvN;
+  };
+
+  // ---- prologue: tables and zeroed buffers (independent of the previous kernel's output)
+  for (int i = tid; i < kWpsWarps * G::kWarpFloats; i += kWpsThreads) smem[i] = 0.0f;
+  for (int i = tid; i < 512; i += kWpsThreads) reinterpret_cast<float4*>(smem + G::sm_tw)[i] = __ldg(tb.tw4 + i);
+  for (int i = tid; i < 256; i += kWpsThreads) reinterpret_cast<float4*>(smem + G::sm_g)[i] = __ldg(tb.g4 + i);
+  for (int i = tid; i < G::kRH; i += kWpsThreads) smem[G::sm_wE + i] = __ldg(tb.wE + i);
+  for (int i = tid; i < G::kRH + 4; i += kWpsThreads) smem[G::sm_wO1 + i] = i > 0 ? __ldg(tb.wO + i - 1) : 0.0f;
+  for (int i = tid; i <= HOP; i += kWpsThreads) smem[G::sm_pw + i] = __ldg(tb.pw + (i == HOP ? 0 : i)) * kInvN;
+  if (tid < kWpsWarps) meta[tid] = 0;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // this warp's range of the flattened frame list
+  const int wi = blockIdx.x * kWpsWarps + warp;
+  const int fa = wp.cut[wi], fb = wp.cut[wi + 1];
+  int u = 0;
+  if (fa < fb) {
+    int lo = 0, hi = bd.B;                                         // largest u with tsum[u] <= fa
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (wp.tsum[mid] <= fa) lo = mid; else hi = mid;
+    }
+    u = lo;
+  }
+  __syncthreads();
+  // programmatic dependent launch: the previous kernel's waveform is complete from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const int partner = (32 - lane) & 31;
+  const bool l0 = lane == 0;
+  int f = fa;
+  while (f < fb) {
+    while (wp.tsum[u + 1] <= f) ++u;                               // skips empty utterances
+    const int tsu = wp.tsum[u];
+    const int T = bd.T[u];
+    const int t_begin = f - tsu;
+    const int t_end = min(T, fb - tsu);
+    f = tsu + t_end;
+    const int L = bd.wav_len[u];
+    if (L <= 0) continue;
+    const long long woff = bd.wav_off[u];
+    const float* __restrict__ src = a.wav_in + woff;
+    float* __restrict__ dst = a.wav_out + woff;
+    const float* spec_row0 = a.spec + bd.frame_off[u] * kF;
+
+    // a run that starts inside the utterance: recompute the overlapping frames (first warp of the CTA) or leave the
+    // first kZone samples as raw partial sums for the end-of-kernel merge with the previous warp's ring
+    int t_first = t_begin;
+    int zone_end = -(1 << 30);
+    if (t_begin > 0) {
+      if (warp == 0) {
+        t_first = max(0, t_begin - G::kWarm);
+      } else {
+        zone_end = (t_begin - 1) * HOP + WIN / 2;
+      }
+    }
+    bool zone_pending = zone_end > 0;
+    float sc_num = 0.0f, sc_den = 0.0f;
+
+    // input span of frame t: samples [a0, a0 + WIN + p) of the utterance, a0 even; asynchronous when it needs no reflection
+    auto span_fast = [&](int t) {
+      const int s0 = t * HOP - WIN / 2;
+      const int a0 = s0 - (s0 & 1);
+      return a0 >= 0 && a0 + WIN + 2 <= L;
+    };
+    auto span_issue = [&](int t) {                                 // returns the landing offset (0 or 2)
+      const int s0 = t * HOP - WIN / 2;
+      const int a0 = s0 - (s0 & 1);
+      return span_to_smem_async_n<WIN + 2>(buf, src + a0, a.wav_in, a.wav_end, lane);
+    };
+    int x_off = 0;
+    if (span_fast(t_first)) x_off = span_issue(t_first);
+    int base = (((t_first * HOP - WIN / 2) >> 1) + WIN) % G::kRH;  // ring slot of the first frame's first pair (a0 / 2, made positive)
+
+#pragma unroll 1
+    for (int t = t_first; t < t_end; ++t) {
+      const int s0 = t * HOP - WIN / 2;
+      const int p = s0 & 1;
+      const int a0 = s0 - p;
+      const bool own = t >= t_begin;
+      const float* const pe = p ? wO1 + lane : wE + lane;          // window of the even / odd sample of pair q = lane + 32 n2
+      const float* const po = p ? wE + lane : wO1 + 1 + lane;
+
+      float2 R[16], I[16];
+      int s_off = 0;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        if (half == 0) {
+          // ---------------------------------------------------------------- input span -> windowed packed frame
+          if (span_fast(t)) {
+            cp_async_wait_all();
+          } else {
+            __syncwarp();
+            for (int m = lane; m < WIN + 2; m += 32) buf[m] = __ldg(src + reflect_index(a0 + m, L));
+            x_off = 0;
+          }
+          __syncwarp();
+          const float2* const xp = reinterpret_cast<const float2*>(buf + x_off) + lane;
+#pragma unroll
+          for (int m = 0; m < 16; ++m) {
+            if (m < G::kMH) {
+              // pairs past the window hold stale exchange data: force zeros (their window taps are zero, but 0 * NaN of
+              // another utterance's bad spectrum must not leak into this one)
+              float2 xa = xp[64 * m];
+              if (64 * m + 31 >= WIN / 2 && lane + 64 * m >= WIN / 2 + p) xa = make_float2(0.0f, 0.0f);
+              float2 xb = make_float2(0.0f, 0.0f), we = make_float2(pe[64 * m], 0.0f), wo = make_float2(po[64 * m], 0.0f);
+              if (2 * m + 1 < G::kRows) {
+                xb = xp[64 * m + 32]; we.y = pe[64 * m + 32]; wo.y = po[64 * m + 32];
+                if (64 * m + 63 >= WIN / 2 && lane + 64 * m + 32 >= WIN / 2 + p) xb = make_float2(0.0f, 0.0f);
+              }
+              R[m] = __fmul2_rn(make_float2(xa.x, xb.x), we);
+              I[m] = __fmul2_rn(make_float2(xa.y, xb.y), wo);
+            } else {
+              R[m] = make_float2(0.0f, 0.0f);
+              I[m] = make_float2(0.0f, 0.0f);
+            }
+          }
+          __syncwarp();                          // the landing zone becomes the exchange buffer
+        } else {
+          // ---------------------------------------------------------------- per-bin step -> conj(Z')   (as frame_kernel)
+          float2 BR[8], BI[8];
+          static_for<0, 8>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            constexpr int ms = (m == 0) ? 0 : 16 - m;
+            const float s0r = l0 ? R[ms].x : R[15 - m].y, s0i = l0 ? I[ms].x : I[15 - m].y;
+            const float s1r = l0 ? R[15 - m].y : R[15 - m].x, s1i = l0 ? I[15 - m].y : I[15 - m].x;
+            BR[m] = shfl2(s0r, s1r, partner);
+            BI[m] = shfl2(s0i, s1i, partner);
+          });
+          cp_async_wait_all();                   // this frame's |S| row (issued between the two forward passes)
+          __syncwarp();
+          const float* srow = buf + s_off;
+          float2 SR[8], SI[8];
+          float2 z512 = make_float2(0.0f, 0.0f);
+          static_for<0, 8>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            const int k0 = 64 * m + lane;
+            const float4 gq = g4[m * 32 + lane];
+            const float2 GX = make_float2(gq.x, gq.y), GY = make_float2(gq.z, gq.w);
+            const float2 Sk = make_float2(spec_to_mag<SRC>(srow[k0], g), spec_to_mag<SRC>(srow[k0 + 32], g));
+            const float2 Sp = make_float2(spec_to_mag<SRC>(srow[1024 - k0], g), spec_to_mag<SRC>(srow[992 - k0], g));
+            const float2 E2R = __fadd2_rn(R[m], BR[m]), E2I = __fadd2_rn(I[m], neg2(BI[m]));
+            const float2 D2R = __fadd2_rn(R[m], neg2(BR[m])), D2I = __fadd2_rn(I[m], BI[m]);
+            float2 XkR = __ffma2_rn(GX, D2R, E2R);
+            XkR = __ffma2_rn(neg2(GY), D2I, XkR);
+            float2 XkI = __ffma2_rn(GX, D2I, E2I);
+            XkI = __ffma2_rn(GY, D2R, XkI);
+            float2 XpR = __ffma2_rn(E2R, splat(2.0f), neg2(XkR));
+            const float2 XpI = __ffma2_rn(E2I, splat(-2.0f), XkI);
+            XkR = __fadd2_rn(XkR, splat(kPhaseEps));               // np.angle(0) = 0 without a select (see frame_kernels.cuh)
+            XpR = __fadd2_rn(XpR, splat(kPhaseEps));
+            const float2 mk = __ffma2_rn(XkI, XkI, __ffma2_rn(XkR, XkR, splat(kTiny)));
+            const float2 mp = __ffma2_rn(XpI, XpI, __ffma2_rn(XpR, XpR, splat(kTiny)));
+            const float2 ik = make_float2(rsqrt_fast(mk.x), rsqrt_fast(mk.y));
+            const float2 ip = make_float2(rsqrt_fast(mp.x), rsqrt_fast(mp.y));
+            const float2 fk = __fmul2_rn(Sk, ik), fp = __fmul2_rn(Sp, ip);
+            const float2 YkR = __fmul2_rn(XkR, fk), YkI = __fmul2_rn(XkI, fk);
+            const float2 YpR = __fmul2_rn(XpR, fp), YpI = __fmul2_rn(XpI, fp);
+            if (SC && own) {
+              const float2 dk = __ffma2_rn(__fmul2_rn(mk, ik), splat(0.5f), neg2(Sk));   // |X| - S
+              const float2 dp = __ffma2_rn(__fmul2_rn(mp, ip), splat(0.5f), neg2(Sp));
+              sc_num += dk.x * dk.x + dk.y * dk.y + dp.x * dp.x + dp.y * dp.y;
+              sc_den += Sk.x * Sk.x + Sk.y * Sk.y + Sp.x * Sp.x + Sp.y * Sp.y;
+            }
+            const float2 PR = __fadd2_rn(YkR, YpR), PI = __fadd2_rn(YkI, neg2(YpI));
+            const float2 DR = __fadd2_rn(YkR, neg2(YpR)), DI = __fadd2_rn(YkI, YpI);
+            float2 vR = __ffma2_rn(GX, DR, PR);
+            vR = __ffma2_rn(GY, DI, vR);
+            float2 vI = __ffma2_rn(neg2(GX), DI, neg2(PI));
+            vI = __ffma2_rn(GY, DR, vI);
+            R[m] = vR; I[m] = vI;
+            SR[m] = __ffma2_rn(PR, splat(2.0f), neg2(vR));
+            SI[m] = __ffma2_rn(PI, splat(2.0f), vI);
+          });
+          if (l0) {   // k = 512 (self-paired): X = conj(Z[512]), conj(Z'2) = 2 Y
+            const float S5 = spec_to_mag<SRC>(srow[512], g);
+            const float2 X = make_float2(R[8].x, -I[8].x);
+            const float m = X.x * X.x + X.y * X.y;
+            const float im = rsqrt_fast(fmaxf(m, kTiny));
+            const float fS = S5 * im;
+            const float2 Y = make_float2(m > kTiny ? X.x * fS : S5, X.y * fS);
+            if (SC && own) {
+              const float d = m * im - S5;
+              sc_num += d * d;
+              sc_den += S5 * S5;
+            }
+            z512 = make_float2(2.0f * Y.x, 2.0f * Y.y);
+          }
+          float rr_[16], ri_[16];
+          static_for<0, 8>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            rr_[2 * m] = __shfl_sync(0xffffffffu, SR[m].x, partner);
+            rr_[2 * m + 1] = __shfl_sync(0xffffffffu, SR[m].y, partner);
+            ri_[2 * m] = __shfl_sync(0xffffffffu, SI[m].x, partner);
+            ri_[2 * m + 1] = __shfl_sync(0xffffffffu, SI[m].y, partner);
+          });
+          static_for<0, 8>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            const float ar = (j == 0) ? z512.x : rr_[(16 - 2 * j) & 15], ai = (j == 0) ? z512.y : ri_[(16 - 2 * j) & 15];
+            R[8 + j] = make_float2(l0 ? ar : rr_[15 - 2 * j], l0 ? rr_[15 - 2 * j] : rr_[14 - 2 * j]);
+            I[8 + j] = make_float2(l0 ? ai : ri_[15 - 2 * j], l0 ? ri_[15 - 2 * j] : ri_[14 - 2 * j]);
+          });
+        }
+
+        // ------------------------------------------------------------------ 1024-point transform, 32 x 32
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          fft32p(R, I);
+          if (pass == 0) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {                        // times W_1024^(lane * k2), k2 = 2m, 2m+1
+              const float4 w = tw4[m * 32 + lane];
+              const float2 WR = make_float2(w.x, w.y), WI = make_float2(w.z, w.w);
+              const float2 nr = __ffma2_rn(R[m], WR, neg2(__fmul2_rn(I[m], WI)));
+              I[m] = __ffma2_rn(R[m], WI, __fmul2_rn(I[m], WR));
+              R[m] = nr;
+            }
+            __syncwarp();                                         // every lane is done with the buffer's previous contents
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {                        // row k2: [re 0..31 | im 0..31], column = lane
+              buf[(2 * m) * kRowFloats + lane] = R[m].x;
+              buf[(2 * m) * kRowFloats + 32 + lane] = I[m].x;
+              buf[(2 * m + 1) * kRowFloats + lane] = R[m].y;
+              buf[(2 * m + 1) * kRowFloats + 32 + lane] = I[m].y;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int jq = 0; jq < 8; ++jq) {
+              const float4 qr = *reinterpret_cast<const float4*>(&buf[lane * kRowFloats + 4 * jq]);
+              const float4 qi = *reinterpret_cast<const float4*>(&buf[lane * kRowFloats + 32 + 4 * jq]);
+              R[2 * jq] = make_float2(qr.x, qr.y); R[2 * jq + 1] = make_float2(qr.z, qr.w);
+              I[2 * jq] = make_float2(qi.x, qi.y); I[2 * jq + 1] = make_float2(qi.z, qi.w);
+            }
+            __syncwarp();
+            // the exchange buffer is idle until the next exchange: land this frame's |S| row (forward half) or the
+            // next frame's input span (inverse half) in it, so that their latency hides behind the coming pass
+            if (half == 0) {
+              s_off = span_to_smem_async_n<kF>(buf, spec_row0 + (long long)t * kF, a.spec, a.spec_end, lane);
+            } else if (t + 1 < t_end && span_fast(t + 1)) {
+              x_off = span_issue(t + 1);
+            }
+          }
+        }
+      }  // halves
+
+      // -------------------------------------------------------------------- window, add into the ring
+      // element n2 = conj(z'[lane + 32 n2]): sample 2q = Re, sample 2q+1 = -Im
+      // (all ring loads first, then the arithmetic, then the stores: loads and stores of the same array cannot be
+      //  reordered by the compiler, and a load-modify-store chain per row would expose the shared-memory latency 18 times)
+      {
+        const int b0 = base + lane;
+        constexpr int kGroup = (G::kRows + 1) / 2;                 // two groups of rows: 2 x 9 accumulators in flight
+#pragma unroll
+        for (int n0 = 0; n0 < G::kRows; n0 += kGroup) {
+          float2 acc[kGroup];
+          int slot[kGroup];
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) {
+            if (n0 + j < G::kRows) {
+              int sl = b0 + 32 * (n0 + j); sl = sl >= G::kRH ? sl - G::kRH : sl;
+              slot[j] = sl;
+              acc[j] = ring[sl];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) {
+            if (n0 + j < G::kRows) {
+              const int n = n0 + j;
+              const float yr = (n & 1) ? R[n >> 1].y : R[n >> 1].x, yi = (n & 1) ? I[n >> 1].y : I[n >> 1].x;
+              acc[j].x = fmaf(pe[32 * n], yr, acc[j].x);
+              acc[j].y = fmaf(-po[32 * n], yi, acc[j].y);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j)
+            if (n0 + j < G::kRows) ring[slot[j]] = acc[j];
+        }
+      }
+      __syncwarp();
+
+      // -------------------------------------------------------------------- finished samples leave the ring
+      const bool last = t == T - 1;                                // the utterance's last frame flushes the whole window
+      const int pn = ((t + 1) * HOP - WIN / 2) & 1;
+      const int count = last ? G::kNP : (HOP + p - pn) >> 1;       // pairs [a0/2, a0(t+1)/2)
+      const bool interior = own && !last && t >= G::kWarm && a0 >= zone_end && a0 >= 0 && a0 + 2 * count <= L;
+      if (interior) {
+        float2 v[G::kEmitIters], inv[G::kEmitIters];
+#pragma unroll
+        for (int it = 0; it < G::kEmitIters; ++it) {
+          const int e = lane + 32 * it;
+          int sl = base + e; sl = sl >= G::kRH ? sl - G::kRH : sl;
+          int r = 2 * e - p; r = r < 0 ? r + HOP : r; r = r >= HOP ? r - HOP : r;
+          v[it] = ring[sl];                                        // (e >= count reads a slot this frame did not finish: ignored)
+          inv[it] = make_float2(pwn[r], pwn[r + 1]);
+        }
+#pragma unroll
+        for (int it = 0; it < G::kEmitIters; ++it) {
+          const int e = lane + 32 * it;
+          if (e < count) {
+            int sl = base + e; sl = sl >= G::kRH ? sl - G::kRH : sl;
+            ring[sl] = make_float2(0.0f, 0.0f);
+            *reinterpret_cast<float2*>(dst + a0 + 2 * e) = make_float2(v[it].x * inv[it].x, v[it].y * inv[it].y);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int e = lane; e < (last ? G::kRH : count); e += 32) { // the last frame leaves the whole ring zero
+          int sl = base + e; sl = sl >= G::kRH ? sl - G::kRH : sl;
+          const float2 v = ring[sl];
+          ring[sl] = make_float2(0.0f, 0.0f);
+          if (own && e < count) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = a0 + 2 * e + h;
+              const float val = h ? v.y : v.x;
+              if (i >= 0 && i < L) dst[i] = i < zone_end ? val : val * inv_wss(i, T);   // raw partial sum inside the head zone
+            }
+          }
+        }
+      }
+      __syncwarp();
+      base += count; base = base >= G::kRH ? base - G::kRH : base;
+      if (zone_pending && own && a0 + 2 * count >= zone_end) {     // the head zone is stored: the previous warp may finish it
+        __threadfence_block();
+        __syncwarp();
+        if (l0) meta[warp] = 1;
+        zone_pending = false;
+      }
+    }  // frames of the run
+
+    if constexpr (SC) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sc_num += __shfl_xor_sync(0xffffffffu, sc_num, o);
+        sc_den += __shfl_xor_sync(0xffffffffu, sc_den, o);
+      }
+      if (lane == 0) {
+        atomicAdd(a.sc_acc + 2 * u, sc_num);
+        atomicAdd(a.sc_acc + 2 * u + 1, sc_den);
+      }
+    }
+    // A run that ends inside the utterance holds the partial sums of the next warp's head zone in its ring: wait until
+    // that warp has stored its share (it does so within its first kWarm + 1 frames, and waits for nobody before), then
+    // finish the zone: out = (its raw partial + this ring) / (N wss).  The last warp of a CTA drops its tail -- the next
+    // CTA's first warp recomputes those frames.
+    if (t_end < T && warp + 1 < kWpsWarps) {
+      const int s0z = t_end * HOP - WIN / 2;
+      const int a0z = s0z - (s0z & 1);
+      const int zend = (t_end - 1) * HOP + WIN / 2;
+      constexpr int kZoneIters = ((G::kZone + 3) / 2 + 31) / 32;
+      while (meta[warp + 1] == 0) __nanosleep(64);
+      __threadfence_block();
+      const bool all_frames = t_end >= G::kWarm && t_end + G::kWarm < T;
+      float2 v[kZoneIters], o[kZoneIters];
+#pragma unroll
+      for (int k = 0; k < kZoneIters; ++k) {
+        const int e = lane + 32 * k;
+        const int i = a0z + 2 * e;
+        int sl = base + e; sl = sl >= G::kRH ? sl - G::kRH : sl;
+        v[k] = make_float2(0.0f, 0.0f); o[k] = v[k];
+        if (i < zend && i >= 0 && i < L) {
+          v[k] = ring[sl];
+          o[k] = ld_volatile_f2(dst + i);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kZoneIters; ++k) {
+        const int e = lane + 32 * k;
+        const int i = a0z + 2 * e;
+        if (i < zend && i >= 0 && i < L) {
+          float2 r2 = o[k];
+          if (all_frames) {
+            int r = (i - s0z) % HOP; r = r < 0 ? r + HOP : r;
+            r2.x = (o[k].x + v[k].x) * pwn[r];
+            if (i + 1 < zend) r2.y = (o[k].y + v[k].y) * pwn[r + 1];
+          } else {
+            r2.x = (o[k].x + v[k].x) * inv_wss(i, T);
+            if (i + 1 < zend && i + 1 < L) r2.y = (o[k].y + v[k].y) * inv_wss(i + 1, T);
+          }
+          *reinterpret_cast<float2*>(dst + i) = r2;
+        }
+      }
+    }
+  }  // runs
+}
+
+}  // namespace ttsa

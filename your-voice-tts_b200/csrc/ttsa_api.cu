@@ -70,6 +70,9 @@ struct ttsa_plan {
   GenGeo gg;
   GenTables gt;
   bool fixed_geo = true;           // use the kernels compiled for this (hop, win) when they exist (TTSA_GENERIC_GEO=1: never)
+  int wps_grid = 0;                // CTAs of the warp-stream kernel (= SMs; TTSA_WPS_GRID overrides it for tests)
+  bool gl_stream = false;          // Griffin-Lim iterations run the warp-stream kernel (gl_stream.cuh) when the batch has a
+                                   // partition for it; TTSA_GL_KERNEL=tile keeps the tile kernel (frame_kernels.cuh)
   // device allocations
   void* d_block = nullptr;         // one allocation holding every table
   const float* d_pinvT = nullptr;  // [num_mels][ldp]
@@ -90,6 +93,11 @@ struct ttsa_batch {
   long long total_frames = 0, total_samples = 0;
   int max_chunks = 0;
   bool dense = true;               // rows of consecutive utterances are contiguous (no per-utterance padding)
+  // warp-stream Griffin-Lim partition: one contiguous range of the flattened frame list per warp of a 16-warp CTA per SM
+  bool wps_ok = false;
+  int wps_grid = 0, wps_win = 0;
+  std::vector<int> wps_cut, tsum;
+  WpsDev wps_dev{nullptr, nullptr};
   void* d_block = nullptr;
   BatchDev dev;
   const int* d_chunk_off = nullptr;
@@ -385,6 +393,11 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     for (int m = r; m < c.win_length; m += c.hop_length) { const double wf = (double)(float)w[m]; acc += wf * wf; }
     h_pw[r] = (float)(1.0 / acc);
   }
+  std::vector<float> h_pw2(2 * (size_t)c.hop_length);          // sample-pair form with the 1/n_fft of the inverse FFT (gl_stream.cuh)
+  for (int r = 0; r < c.hop_length; ++r) {
+    h_pw2[2 * r] = h_pw[r] * (1.0f / (float)kNfft);
+    h_pw2[2 * r + 1] = h_pw[(r + 1) % c.hop_length] * (1.0f / (float)kNfft);
+  }
   // shared-memory image of the frame kernels' constant tables (Layout: [sm_wE, sm_mbar))
   const Layout& ly = p->geo.ly;
   std::vector<float> h_img(ly.image_floats, 0.f);
@@ -447,7 +460,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       {h_wE2.data(), h_wE2.size() * 4, 0}, {h_wO2.data(), h_wO2.size() * 4, 0},
       {h_pinv_tc.data(), h_pinv_tc.size() * 2, 0}, {h_mel_tc.data(), h_mel_tc.size() * 2, 0},
       {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}, {h_img.data(), h_img.size() * 4, 0},
-      {h_melc.data(), h_melc.size() * 4, 0}};
+      {h_melc.data(), h_melc.size() * 4, 0}, {h_pw2.data(), h_pw2.size() * 4, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -471,6 +484,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->tb.wE = (const float*)(base + pieces[2].off);
   p->tb.wO = (const float*)(base + pieces[3].off);
   p->tb.pw = (const float*)(base + pieces[4].off);
+  p->tb.pw2 = (const float2*)(base + pieces[16].off);
   p->tb.mel_lo = (const int*)(base + pieces[5].off);
   p->tb.mel_cnt = (const int*)(base + pieces[6].off);
   p->tb.mel_val = (const float*)(base + pieces[7].off);
@@ -483,6 +497,16 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   const char* err = configure_frame_kernels(smem_bytes, &occ);
   if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
   p->ctas_per_sm = occ < 1 ? 1 : occ;
+  if (gl_stream_supported(c.hop_length, c.win_length)) {
+    const char* gk = std::getenv("TTSA_GL_KERNEL");
+    p->gl_stream = !(gk != nullptr && std::strcmp(gk, "tile") == 0);
+    const char* wg = std::getenv("TTSA_WPS_GRID");
+    p->wps_grid = (wg != nullptr && std::atoi(wg) > 0) ? std::min(std::atoi(wg), p->num_sms) : p->num_sms;
+    if (p->gl_stream) {
+      err = configure_gl_stream();
+      if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
+    }
+  }
   { const char* gen = std::getenv("TTSA_GENERIC_GEO"); p->fixed_geo = !(gen != nullptr && std::atoi(gen) != 0); }
   { const char* dbg = std::getenv("TTSA_DEBUG"); p->debug = dbg ? std::atoi(dbg) : 0; }
   { const char* mg = std::getenv("TTSA_MEL_GEMM");
@@ -521,6 +545,59 @@ extern "C" int ttsa_plan_inv_mel_basis(const ttsa_plan* plan, double* host_out) 
 // ---------------------------------------------------------------------------------------------------------
 // batch layout
 // ---------------------------------------------------------------------------------------------------------
+// Partition of the flattened frame list for the warp-stream Griffin-Lim kernel: `grid` CTAs x 16 warps, one contiguous
+// range per warp.  CTA ranges are proportional; inside a CTA the first warp gets `warm` frames less (it recomputes that
+// many frames before its range when the range starts inside an utterance).  A cut closer than `minrun` frames to an
+// utterance boundary is moved onto the boundary, so every run that both starts and ends inside an utterance is at least
+// `minrun` frames long (the kernel's pairwise merge of neighbouring warps relies on it).  Returns false when the batch
+// is too small for that (the tile kernel serves it).
+static bool build_wps_partition(const std::vector<int>& T, int hop, int win, int grid, std::vector<int>& tsum, std::vector<int>& cut) {
+  const int B = (int)T.size();
+  const int warm = (win - 1) / hop, minrun = warm + 1;
+  tsum.assign(B + 1, 0);
+  long long total = 0;
+  for (int u = 0; u < B; ++u) {
+    total += T[u];
+    if (total > 0x3fffffff) return false;
+    tsum[u + 1] = (int)total;
+  }
+  const int G = (int)total;
+  const int nw = grid * 16;
+  if (grid <= 0 || (long long)G < (long long)nw * (2 * minrun)) return false;
+  cut.assign(nw + 1, 0);
+  for (int c = 0; c < grid; ++c) {
+    const long long lo = (long long)c * G / grid, hi = (long long)(c + 1) * G / grid;
+    const long long n = hi - lo;
+    long long n0 = (n + warm) / 16 - warm;                 // first warp: equal COST including its warm-up frames
+    if (n0 < minrun) n0 = minrun;
+    cut[c * 16] = (int)lo;
+    for (int j = 1; j < 16; ++j) cut[c * 16 + j] = (int)(lo + n0 + (long long)(j - 1) * (n - n0) / 15);
+  }
+  cut[nw] = G;
+  // snap to utterance boundaries, keep the list monotone
+  int u = 0;
+  for (int i = 1; i < nw; ++i) {
+    int x = cut[i];
+    while (u + 1 < B && tsum[u + 1] <= x) ++u;
+    if (x - tsum[u] < minrun) x = tsum[u];
+    else if (tsum[u + 1] - x < minrun) x = tsum[u + 1];
+    cut[i] = x < cut[i - 1] ? cut[i - 1] : x;
+  }
+  // verify: two cuts strictly inside the same utterance are at least minrun apart
+  u = 0;
+  for (int i = 1; i <= nw; ++i) {
+    if (cut[i] < cut[i - 1]) return false;
+    if (cut[i] == cut[i - 1]) continue;
+    while (u + 1 < B && tsum[u + 1] <= cut[i - 1]) ++u;
+    const bool prev_inside = cut[i - 1] > tsum[u];
+    const bool cur_inside_same = cut[i] < tsum[u + 1];
+    if (prev_inside && cur_inside_same && cut[i] - cut[i - 1] < minrun) return false;
+    if (prev_inside && cut[i - 1] - tsum[u] < minrun) return false;
+    if (cur_inside_same && tsum[u + 1] - cut[i] < minrun) return false;
+  }
+  return true;
+}
+
 static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, long long frame_stride = 0) {
   const int B = b->B;
   b->device = plan->device;
@@ -544,9 +621,15 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
   std::memset(&b->dev, 0, sizeof(b->dev));
   b->dev.B = B;
   b->dev.total_tiles = b->tile_off[B];
+  if (plan->device >= 0 && plan->gl_stream) {
+    b->wps_grid = plan->wps_grid;
+    b->wps_win = plan->cfg.win_length;
+    b->wps_ok = build_wps_partition(b->T, b->hop, b->wps_win, b->wps_grid, b->tsum, b->wps_cut);
+  }
   if (plan->device >= 0) {
     DeviceGuard guard(plan->device);
-    const size_t n_i = (size_t)B * 2 + (size_t)(B + 1) * 2;     // T, wav_len, tile_off, chunk_off
+    const size_t n_wps = b->wps_ok ? b->tsum.size() + b->wps_cut.size() : 0;
+    const size_t n_i = (size_t)B * 2 + (size_t)(B + 1) * 2 + n_wps;     // T, wav_len, tile_off, chunk_off, [tsum, wps_cut]
     const size_t bytes_i = (n_i * 4 + 15) / 16 * 16;
     const size_t bytes_l = (size_t)(B + 1) * 2 * 8;
     if (cudaMalloc(&b->d_block, bytes_i + bytes_l) != cudaSuccess) { delete b; return fail(TTSA_ERR_CUDA, "cudaMalloc for batch layout failed"); }
@@ -559,6 +642,10 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
     std::memcpy(hi + B, b->wav_len.data(), B * 4);
     std::memcpy(hi + 2 * B, b->tile_off.data(), (B + 1) * 4);
     std::memcpy(hi + 2 * B + (B + 1), b->chunk_off.data(), (B + 1) * 4);
+    if (b->wps_ok) {
+      std::memcpy(hi + 2 * B + 2 * (B + 1), b->tsum.data(), b->tsum.size() * 4);
+      std::memcpy(hi + 2 * B + 3 * (B + 1), b->wps_cut.data(), b->wps_cut.size() * 4);
+    }
     cudaError_t e = cudaMemcpy(b->d_block, h.data(), h.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(b->d_block); delete b; return fail(TTSA_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e)); }
     const long long* dl = (const long long*)b->d_block;
@@ -569,6 +656,7 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
     b->dev.wav_len = di + B;
     b->dev.tile_off = di + 2 * B;
     b->d_chunk_off = di + 2 * B + (B + 1);
+    if (b->wps_ok) { b->wps_dev.tsum = di + 2 * B + 2 * (B + 1); b->wps_dev.cut = di + 2 * B + 3 * (B + 1); }
   }
   *out = b;
   return TTSA_OK;
@@ -895,7 +983,11 @@ extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* ba
     b.wav_end = b.wav_in + batch->total_samples;
     b.debug = plan->debug;
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
-    if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st, mom_i)) {
+    if (!mom_i && plan->gl_stream && plan->fixed_geo && plan->debug == 0 && batch->wps_ok && batch->wps_win == plan->cfg.win_length) {
+      const char* err = launch_gl_stream(spec_kind, sc_log_dev != nullptr, plan->cfg.hop_length, plan->cfg.win_length, batch->wps_grid,
+                                         st, plan->geo, plan->tb, batch->dev, batch->wps_dev, b);
+      if (err) return fail(TTSA_ERR_CUDA, "Griffin-Lim stream kernel launch: %s", err);
+    } else if (int rc = launch_frames(plan, batch, MODE_GL_ITER, spec_kind, sc_log_dev != nullptr, b, st, mom_i)) {
       return rc;
     }
   }
