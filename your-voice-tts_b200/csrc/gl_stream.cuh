@@ -18,11 +18,13 @@
 // transform undo exactly (the same argument as the window-relative coordinates of frame_kernels.cuh).
 //
 // Run boundaries.  The host cuts the flattened frame list into one contiguous range per warp (ttsa_batch, wps_cut).
-// A range that starts in the middle of an utterance lacks the contributions of the `kWarm` frames before it:
-//   * first warp of a CTA: those frames are recomputed (no output), as frame_kernel does per CTA segment;
-//   * any other warp: its first win - hop samples are stored as RAW partial sums; the previous warp of the same CTA
-//     keeps the matching partial sums in its ring, and after one CTA barrier at the very end the zone is finished
-//     (sum, * 1/(N wss)) -- every output sample is still written by a fixed thread in a fixed order: deterministic.
+// A range that starts in the middle of an utterance lacks the contributions of the `kWarm` frames before it: its first
+// win - hop samples (the "head zone") are stored as RAW partial sums and the warp then publishes a flag in global memory
+// (release); the warp that owns the frames before the cut -- in this CTA or in the previous one -- keeps the matching
+// partial sums in its ring and, at the very end of its run, waits for that flag (acquire), adds the two halves and
+// applies 1/(N wss).  Nothing is recomputed, every output sample is still written last by a fixed thread with a fixed
+// summation order (deterministic), and the only wait is on a warp that published its zone a whole run earlier.  The
+// waiting warp depends on a warp that itself waits for nobody before publishing, so CTAs need not be co-resident.
 #pragma once
 #include "frame_kernels.cuh"
 
@@ -31,9 +33,17 @@ namespace ttsa {
 constexpr int kWpsWarps = 16;
 constexpr int kWpsThreads = kWpsWarps * 32;
 
-__device__ __forceinline__ float2 ld_volatile_f2(const float* p) {
+__device__ __forceinline__ float2 ld_volatile_f2(const float* p) {        // another SM wrote it: read through L2
   float2 v;
-  asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -57,8 +67,7 @@ struct WpsGeo {
   static constexpr int sm_wE = sm_g + 1024;                      // [kRH]      w[2q]
   static constexpr int sm_wO1 = sm_wE + kRH;                     // [kRH + 4]  w[2(q-1)+1], entry 0 = 0
   static constexpr int sm_pw = sm_wO1 + kRH + 4;                 // [HOP + 1]  1 / (n_fft wss), entry HOP = entry 0
-  static constexpr int sm_meta = sm_pw + (HOP + 4) / 4 * 4;      // int[kWpsWarps]: "head zone stored" flag per warp
-  static constexpr int sm_total = sm_meta + kWpsWarps;
+  static constexpr int sm_total = sm_pw + (HOP + 4) / 4 * 4;
 };
 
 template <int SRC, bool SC, int HOP, int WIN>
@@ -78,7 +87,6 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
   const float* const wE = smem + G::sm_wE;
   const float* const wO1 = smem + G::sm_wO1;
   const float* const pwn = smem + G::sm_pw;
-  volatile int* const meta = reinterpret_cast<volatile int*>(smem + G::sm_meta);
 
   // 1 / (n_fft * window sum of squares) at sample i of an utterance with T frames, over the frames that exist
   // (librosa: divide only where wss > tiny); the interior uses the periodic table pwn instead
@@ -102,7 +110,6 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
   for (int i = tid; i < G::kRH; i += kWpsThreads) smem[G::sm_wE + i] = __ldg(tb.wE + i);
   for (int i = tid; i < G::kRH + 4; i += kWpsThreads) smem[G::sm_wO1 + i] = i > 0 ? __ldg(tb.wO + i - 1) : 0.0f;
   for (int i = tid; i <= HOP; i += kWpsThreads) smem[G::sm_pw + i] = __ldg(tb.pw + (i == HOP ? 0 : i)) * kInvN;
-  if (tid < kWpsWarps) meta[tid] = 0;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // this warp's range of the flattened frame list
@@ -138,17 +145,9 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
     float* __restrict__ dst = a.wav_out + woff;
     const float* spec_row0 = a.spec + bd.frame_off[u] * kF;
 
-    // a run that starts inside the utterance: recompute the overlapping frames (first warp of the CTA) or leave the
-    // first kZone samples as raw partial sums for the end-of-kernel merge with the previous warp's ring
-    int t_first = t_begin;
-    int zone_end = -(1 << 30);
-    if (t_begin > 0) {
-      if (warp == 0) {
-        t_first = max(0, t_begin - G::kWarm);
-      } else {
-        zone_end = (t_begin - 1) * HOP + WIN / 2;
-      }
-    }
+    // a run that starts inside the utterance leaves its first kZone samples as raw partial sums; the owner of the
+    // frames before the cut finishes them at the end of its run
+    const int zone_end = t_begin > 0 ? (t_begin - 1) * HOP + WIN / 2 : -(1 << 30);
     bool zone_pending = zone_end > 0;
     float sc_num = 0.0f, sc_den = 0.0f;
 
@@ -164,15 +163,14 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       return span_to_smem_async_n<WIN + 2>(buf, src + a0, a.wav_in, a.wav_end, lane);
     };
     int x_off = 0;
-    if (span_fast(t_first)) x_off = span_issue(t_first);
-    int base = (((t_first * HOP - WIN / 2) >> 1) + WIN) % G::kRH;  // ring slot of the first frame's first pair (a0 / 2, made positive)
+    if (span_fast(t_begin)) x_off = span_issue(t_begin);
+    int base = (((t_begin * HOP - WIN / 2) >> 1) + WIN) % G::kRH;  // ring slot of the first frame's first pair (a0 / 2, made positive)
 
 #pragma unroll 1
-    for (int t = t_first; t < t_end; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
       const int s0 = t * HOP - WIN / 2;
       const int p = s0 & 1;
       const int a0 = s0 - p;
-      const bool own = t >= t_begin;
       const float* const pe = p ? wO1 + lane : wE + lane;          // window of the even / odd sample of pair q = lane + 32 n2
       const float* const po = p ? wE + lane : wO1 + 1 + lane;
 
@@ -251,7 +249,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             const float2 fk = __fmul2_rn(Sk, ik), fp = __fmul2_rn(Sp, ip);
             const float2 YkR = __fmul2_rn(XkR, fk), YkI = __fmul2_rn(XkI, fk);
             const float2 YpR = __fmul2_rn(XpR, fp), YpI = __fmul2_rn(XpI, fp);
-            if (SC && own) {
+            if (SC) {
               const float2 dk = __ffma2_rn(__fmul2_rn(mk, ik), splat(0.5f), neg2(Sk));   // |X| - S
               const float2 dp = __ffma2_rn(__fmul2_rn(mp, ip), splat(0.5f), neg2(Sp));
               sc_num += dk.x * dk.x + dk.y * dk.y + dp.x * dp.x + dp.y * dp.y;
@@ -274,7 +272,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             const float im = rsqrt_fast(fmaxf(m, kTiny));
             const float fS = S5 * im;
             const float2 Y = make_float2(m > kTiny ? X.x * fS : S5, X.y * fS);
-            if (SC && own) {
+            if (SC) {
               const float d = m * im - S5;
               sc_num += d * d;
               sc_den += S5 * S5;
@@ -377,7 +375,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       const bool last = t == T - 1;                                // the utterance's last frame flushes the whole window
       const int pn = ((t + 1) * HOP - WIN / 2) & 1;
       const int count = last ? G::kNP : (HOP + p - pn) >> 1;       // pairs [a0/2, a0(t+1)/2)
-      const bool interior = own && !last && t >= G::kWarm && a0 >= zone_end && a0 >= 0 && a0 + 2 * count <= L;
+      const bool interior = !last && t >= G::kWarm && a0 >= zone_end && a0 >= 0 && a0 + 2 * count <= L;
       if (interior) {
         float2 v[G::kEmitIters], inv[G::kEmitIters];
 #pragma unroll
@@ -403,7 +401,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
           int sl = base + e; sl = sl >= G::kRH ? sl - G::kRH : sl;
           const float2 v = ring[sl];
           ring[sl] = make_float2(0.0f, 0.0f);
-          if (own && e < count) {
+          if (e < count) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int i = a0 + 2 * e + h;
@@ -415,10 +413,10 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       }
       __syncwarp();
       base += count; base = base >= G::kRH ? base - G::kRH : base;
-      if (zone_pending && own && a0 + 2 * count >= zone_end) {     // the head zone is stored: the previous warp may finish it
-        __threadfence_block();
+      if (zone_pending && a0 + 2 * count >= zone_end) {            // the head zone is stored: the owner of the frames before
+        __threadfence();                                           // the cut may finish it (release at gpu scope)
         __syncwarp();
-        if (l0) meta[warp] = 1;
+        if (l0) st_release_gpu(a.wps_flags + wi, a.wps_epoch);
         zone_pending = false;
       }
     }  // frames of the run
@@ -434,17 +432,18 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
         atomicAdd(a.sc_acc + 2 * u + 1, sc_den);
       }
     }
-    // A run that ends inside the utterance holds the partial sums of the next warp's head zone in its ring: wait until
-    // that warp has stored its share (it does so within its first kWarm + 1 frames, and waits for nobody before), then
-    // finish the zone: out = (its raw partial + this ring) / (N wss).  The last warp of a CTA drops its tail -- the next
-    // CTA's first warp recomputes those frames.
-    if (t_end < T && warp + 1 < kWpsWarps) {
+    // A run that ends inside the utterance holds the partial sums of the next run's head zone in its ring: wait until
+    // that run's warp (the next one with a non-empty range; possibly in the next CTA) has stored its share -- it does so
+    // within its first kWarm + 1 frames, and waits for nobody before -- then finish the zone:
+    // out = (its raw partial + this ring) / (N wss).
+    if (t_end < T) {
       const int s0z = t_end * HOP - WIN / 2;
       const int a0z = s0z - (s0z & 1);
       const int zend = (t_end - 1) * HOP + WIN / 2;
       constexpr int kZoneIters = ((G::kZone + 3) / 2 + 31) / 32;
-      while (meta[warp + 1] == 0) __nanosleep(64);
-      __threadfence_block();
+      int nx = wi + 1;
+      while (wp.cut[nx + 1] == wp.cut[nx]) ++nx;                   // the cut list ends at the total frame count > cut[nx]
+      while (ld_acquire_gpu(a.wps_flags + nx) != a.wps_epoch) __nanosleep(64);
       const bool all_frames = t_end >= G::kWarm && t_end + G::kWarm < T;
       float2 v[kZoneIters], o[kZoneIters];
 #pragma unroll

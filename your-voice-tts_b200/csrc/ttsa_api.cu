@@ -542,15 +542,14 @@ extern "C" int ttsa_plan_inv_mel_basis(const ttsa_plan* plan, double* host_out) 
   return TTSA_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// batch layout
-// ---------------------------------------------------------------------------------------------------------
-// Partition of the flattened frame list for the warp-stream Griffin-Lim kernel: `grid` CTAs x 16 warps, one contiguous
-// range per warp.  CTA ranges are proportional; inside a CTA the first warp gets `warm` frames less (it recomputes that
-// many frames before its range when the range starts inside an utterance).  A cut closer than `minrun` frames to an
-// utterance boundary is moved onto the boundary, so every run that both starts and ends inside an utterance is at least
-// `minrun` frames long (the kernel's pairwise merge of neighbouring warps relies on it).  Returns false when the batch
-// is too small for that (the tile kernel serves it).
+// Work partition of the warp-stream Griffin-Lim kernel: the flattened frame list (utterance after utterance) is cut into
+// one contiguous range per warp.  A range that starts inside an utterance hands its first win - hop samples over to the
+// owner of the frames before the cut (gl_stream.cuh), which works when that owner holds ALL `warm` frames that overlap
+// the cut: a run that both starts and ends inside one utterance must be at least `minrun` frames long, and no cut may lie
+// closer than `minrun` frames to an utterance boundary.  Balance matters more than anything else here (the launch ends
+// with its longest run): cuts start evenly spaced, cuts too close to a boundary snap onto it, and the cuts between two
+// consecutive boundary cuts of the same utterance are then re-spaced evenly, so run lengths differ by at most one frame
+// wherever utterances are longer than a run.  Returns false when the batch is too small (the tile kernel serves it).
 static bool build_wps_partition(const std::vector<int>& T, int hop, int win, int grid, std::vector<int>& tsum, std::vector<int>& cut) {
   const int B = (int)T.size();
   const int warm = (win - 1) / hop, minrun = warm + 1;
@@ -565,16 +564,10 @@ static bool build_wps_partition(const std::vector<int>& T, int hop, int win, int
   const int nw = grid * 16;
   if (grid <= 0 || (long long)G < (long long)nw * (2 * minrun)) return false;
   cut.assign(nw + 1, 0);
-  for (int c = 0; c < grid; ++c) {
-    const long long lo = (long long)c * G / grid, hi = (long long)(c + 1) * G / grid;
-    const long long n = hi - lo;
-    long long n0 = (n + warm) / 16 - warm;                 // first warp: equal COST including its warm-up frames
-    if (n0 < minrun) n0 = minrun;
-    cut[c * 16] = (int)lo;
-    for (int j = 1; j < 16; ++j) cut[c * 16 + j] = (int)(lo + n0 + (long long)(j - 1) * (n - n0) / 15);
-  }
-  cut[nw] = G;
+  for (int i = 0; i <= nw; ++i) cut[i] = (int)((long long)i * G / nw);
   // snap to utterance boundaries, keep the list monotone
+  std::vector<char> on_boundary(nw + 1, 0);
+  on_boundary[0] = on_boundary[nw] = 1;
   int u = 0;
   for (int i = 1; i < nw; ++i) {
     int x = cut[i];
@@ -583,7 +576,25 @@ static bool build_wps_partition(const std::vector<int>& T, int hop, int win, int
     else if (tsum[u + 1] - x < minrun) x = tsum[u + 1];
     cut[i] = x < cut[i - 1] ? cut[i - 1] : x;
   }
-  // verify: two cuts strictly inside the same utterance are at least minrun apart
+  u = 0;
+  for (int i = 1; i < nw; ++i) {
+    while (u + 1 < B && tsum[u + 1] <= cut[i]) ++u;
+    on_boundary[i] = cut[i] == tsum[u];
+  }
+  // re-space the cuts strictly between two boundary cuts that delimit (part of) ONE utterance
+  for (int ia = 0; ia < nw;) {
+    int ib = ia + 1;
+    while (!on_boundary[ib]) ++ib;
+    const int a = cut[ia], b = cut[ib], n = ib - ia;
+    if (n > 1 && b > a) {
+      int ua = 0;
+      { int lo = 0, hi = B; while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tsum[mid] <= a) lo = mid; else hi = mid; } ua = lo; }
+      if (b <= tsum[ua + 1] && (long long)(b - a) >= (long long)n * minrun)
+        for (int i = ia + 1; i < ib; ++i) cut[i] = a + (int)((long long)(i - ia) * (b - a) / n);
+    }
+    ia = ib;
+  }
+  // verify: two cuts strictly inside the same utterance are at least minrun apart, and minrun away from its ends
   u = 0;
   for (int i = 1; i <= nw; ++i) {
     if (cut[i] < cut[i - 1]) return false;
@@ -782,10 +793,15 @@ extern "C" size_t ttsa_deemphasis_workspace_bytes(const ttsa_plan* plan, const t
   return ((size_t)batch->chunk_off[batch->B] * 4 + 255) / 256 * 256 + 256;
 }
 
+static size_t wps_flag_bytes(const ttsa_batch* batch) {
+  return batch->wps_ok ? ((size_t)batch->wps_grid * 16 * 4 + 255) / 256 * 256 : 0;
+}
+
 extern "C" size_t ttsa_griffin_lim_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* batch) {
   if (!plan || !batch) return 0;
   const size_t wav = ((size_t)batch->total_samples * 4 + 255) / 256 * 256 + 256;
-  return 3 * wav + ttsa_deemphasis_workspace_bytes(plan, batch);     // two estimates + one more for the momentum mode
+  // two estimates + one more for the momentum mode, the de-emphasis aggregates, the warp flags of the stream kernel
+  return 3 * wav + ttsa_deemphasis_workspace_bytes(plan, batch) + wps_flag_bytes(batch);
 }
 
 static int deemph_launch(const ttsa_plan* plan, const ttsa_batch* batch, const float* x, float* y, float* agg, cudaStream_t st) {
@@ -939,6 +955,7 @@ extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* ba
   float* wsB = (float*)((char*)workspace_dev + wav_bytes);
   float* wsC = (float*)((char*)workspace_dev + 2 * wav_bytes);
   float* agg = (float*)((char*)workspace_dev + 3 * wav_bytes);
+  int* wps_flags = (int*)((char*)agg + ttsa_deemphasis_workspace_bytes(plan, batch));
   // write k (0 = initial istft, 1..iters = iterations) goes to bufs[k % nb]; the last one must land in `last`.
   // nb = 2 (ping-pong), or 3 with momentum: iteration k reads estimates k-1 and k-2.
   const bool mom = momentum > 0.0 && iters > 1;
@@ -954,6 +971,9 @@ extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* ba
     for (int i = 0, k = 0; i < nb; ++i) if (bufs[i] == nullptr) bufs[i] = spare[k++];
   }
   if (sc_log_dev && iters > 0) CUDA_TRY(cudaMemsetAsync(sc_log_dev, 0, (size_t)iters * batch->B * 2 * 4, st));
+  const bool use_stream = !plan->generic && plan->gl_stream && plan->fixed_geo && plan->debug == 0 && batch->wps_ok &&
+                          batch->wps_win == plan->cfg.win_length;
+  if (use_stream && iters > 0) CUDA_TRY(cudaMemsetAsync(wps_flags, 0, wps_flag_bytes(batch), st));
 
   if (plan->generic) {
     FrameArgs a{};
@@ -983,7 +1003,8 @@ extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* ba
     b.wav_end = b.wav_in + batch->total_samples;
     b.debug = plan->debug;
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
-    if (!mom_i && plan->gl_stream && plan->fixed_geo && plan->debug == 0 && batch->wps_ok && batch->wps_win == plan->cfg.win_length) {
+    if (!mom_i && use_stream) {
+      b.wps_flags = wps_flags; b.wps_epoch = i;
       const char* err = launch_gl_stream(spec_kind, sc_log_dev != nullptr, plan->cfg.hop_length, plan->cfg.win_length, batch->wps_grid,
                                          st, plan->geo, plan->tb, batch->dev, batch->wps_dev, b);
       if (err) return fail(TTSA_ERR_CUDA, "Griffin-Lim stream kernel launch: %s", err);
