@@ -5,7 +5,8 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_in
                     c_void_p)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libttsa_b200.so")
+# TTSA_LIB: A/B experiments against a second build (build.py with TTSA_BUILD_TAG); the shipped library otherwise
+LIB_PATH = os.environ.get("TTSA_LIB") or os.path.join(HERE, "libttsa_b200.so")
 
 TTSA_OK = 0
 TTSA_ERR_BAD_ARG = -1

@@ -13,11 +13,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libttsa_b200.so")
+TAG = os.environ.get("TTSA_BUILD_TAG", "")                # experiments only: a second library next to the shipped one
+OBJ = os.path.join(HERE, "build" + TAG)
+LIB = os.path.join(HERE, "libttsa_b200%s.so" % TAG)
 SOURCES = ["ttsa_api.cu", "gl_stream.cu", "frame_gl.cu", "frame_gl_mom.cu", "frame_synth.cu", "frame_analysis.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+EXTRA = os.environ.get("TTSA_NVCC_EXTRA", "").split()      # experiments only (e.g. -DTTSA_WPS_WARPS=8)
+FLAGS = EXTRA + ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-Xcudafe", "--diag_suppress=940"]
 
 

@@ -83,6 +83,7 @@ struct Tables {
   const float* wO;       // [1024]    w[2q+1]
   const float* pw;       // [hop]    1 / sum_q w[r + q*hop]^2   (interior window-sum-square, periodic in hop)
   const float2* pw2;     // [hop]    (pw[r], pw[(r + 1) % hop]) / n_fft   (sample pairs of the warp-stream Griffin-Lim kernel)
+  const float* wps_image;   // table image of the warp-stream Griffin-Lim kernel (gl_stream.cuh, WpsGeo): tw4 | g4 | wE | wO1 | pwx
   const float* smem_image;  // [Layout::image_floats]  wE2 | wO2 | pw / n_fft | signed synthesis window | tw4 | g4, laid out
                             // exactly as the kernels keep them in shared memory (one bulk copy per CTA)
   // sparse mel basis (CSR over mel rows; each row is one contiguous run of bins)
@@ -105,10 +106,16 @@ struct BatchDev {
   int total_tiles;
 };
 
+#ifndef TTSA_WPS_WARPS
+#define TTSA_WPS_WARPS 16
+#endif
+constexpr int kWpsWarps = TTSA_WPS_WARPS;   // warps per CTA (one CTA per SM) of the warp-stream Griffin-Lim kernel
+
 // Work partition of the warp-stream Griffin-Lim kernel (gl_stream.cuh), built by the host with the batch.
 struct WpsDev {
-  const int* cut;     // [grid * 16 + 1] flattened frame index where each warp's range starts (non-decreasing)
+  const int* cut;     // [grid * kWpsWarps + 1] flattened frame index where each warp's range starts (non-decreasing)
   const int* tsum;    // [B + 1] prefix sum of the frame counts (flattened frame index of each utterance's frame 0)
+  const int* u0;      // [grid * kWpsWarps] utterance that holds the first frame of each warp's range
 };
 
 __device__ __forceinline__ int reflect_index(int i, int L) {

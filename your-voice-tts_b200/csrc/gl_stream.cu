@@ -25,6 +25,7 @@ static const char* launch_one(int grid, cudaStream_t st, const Geo& g, const Tab
 
 template <int HOP, int WIN>
 static const char* configure_geo() {
+  if constexpr (!WpsGeo<HOP, WIN>::kFits) return nullptr;
   const char* e;
   if ((e = set_smem(gl_stream_kernel<SRC_MAG, false, HOP, WIN>, 0))) return e;
   if ((e = set_smem(gl_stream_kernel<SRC_MAG, true, HOP, WIN>, 0))) return e;
@@ -35,6 +36,8 @@ static const char* configure_geo() {
 template <int HOP, int WIN>
 static const char* launch_geo(int src, bool sc, int grid, cudaStream_t st, const Geo& g, const Tables& tb, const BatchDev& bd,
                               const WpsDev& wp, const FrameArgs& a) {
+  if constexpr (!WpsGeo<HOP, WIN>::kFits) return "gl_stream: geometry does not fit shared memory";
+  else
   if (src == SRC_MAG) return sc ? launch_one<SRC_MAG, true, HOP, WIN>(grid, st, g, tb, bd, wp, a)
                                 : launch_one<SRC_MAG, false, HOP, WIN>(grid, st, g, tb, bd, wp, a);
   return sc ? launch_one<SRC_NORM_DB, true, HOP, WIN>(grid, st, g, tb, bd, wp, a)
@@ -42,7 +45,7 @@ static const char* launch_geo(int src, bool sc, int grid, cudaStream_t st, const
 }
 
 bool gl_stream_supported(int hop, int win) {
-#define TTSA_X(H, W) if (hop == H && win == W) return true;
+#define TTSA_X(H, W) if (hop == H && win == W) return WpsGeo<H, W>::kFits;
   TTSA_FIXED_GEOS(TTSA_X)
 #undef TTSA_X
   return false;

@@ -3,8 +3,10 @@
 // has no CTA-wide barrier, no shared staging buffer and no separate overlap-add phase:
 //
 //   per frame (one warp):  cp.async'ed input span -> window -> FFT (32 x 32, one exchange) -> |S| e^{j angle X}
-//                          -> inverse FFT (same code, conjugate trick) -> window, add into the ring
-//                          -> the hop samples no later frame touches leave the ring: * 1/(N wss) -> global
+//                          -> inverse FFT (same code, conjugate trick) -> window, ONE pass over the ring:
+//                             the hop samples no later frame touches get their last term, * 1/(N wss) -> global;
+//                             the rest is accumulated in place; the part of the window no earlier frame reached is
+//                             stored without a load (so the ring never needs zeroing)
 //
 // The 16 warps of the one CTA per SM drift apart and sit in different phases (FP32-bound transform passes,
 // shared-memory-bound exchanges, latency-bound per-bin step), which is what keeps the pipes busy; frame_kernel<GL_ITER>
@@ -30,7 +32,6 @@
 
 namespace ttsa {
 
-constexpr int kWpsWarps = 16;
 constexpr int kWpsThreads = kWpsWarps * 32;
 
 __device__ __forceinline__ float2 ld_volatile_f2(const float* p) {        // another SM wrote it: read through L2
@@ -47,6 +48,13 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
+// Timing probes (experiment builds only, -DTTSA_PROBE=mask: results are wrong on purpose): 1 no 32-point passes,
+// 2 no inter-pass twiddles, 4 no exchange, 8 no per-bin step, 16 no ring accumulation, 32 no emission, 64 no input load, 128 no asynchronous copies (|S| rows, input spans)
+#ifndef TTSA_PROBE
+#define TTSA_PROBE 0
+#endif
+constexpr int kProbe = TTSA_PROBE;
+
 template <int HOP, int WIN>
 struct WpsGeo {
   static_assert(WIN % 2 == 0 && HOP >= 2 && WIN >= HOP, "even window not shorter than the hop");
@@ -60,14 +68,22 @@ struct WpsGeo {
   static constexpr int kEmitIters = ((HOP + 1) / 2 + 31) / 32;
   static constexpr int kFlushIters = (kNP + 31) / 32;
   static_assert(kRows <= 20, "window too long for this kernel");
-  // shared memory (floats)
+  static constexpr int kCntMin = HOP / 2, kCntMax = (HOP + 1) / 2;   // pairs that leave the ring per interior frame
+  static constexpr int kEmitRows = (kCntMax + 31) / 32;
+  static constexpr int kPwx = (64 * kEmitRows + 4 + 3) / 4 * 4;  // entries of the shifted 1/(N wss) table
+  static_assert(kPwx >= HOP + 2, "hop too long for the emission table");
+  // shared memory (floats): per-warp buffers, then the constant tables as ONE host-built image (Tables::wps_image)
   static constexpr int kWarpFloats = kBufFloats + 2 * kRH;
-  static constexpr int sm_tw = kWpsWarps * kWarpFloats;          // float4[16][32]
+  static constexpr int sm_img = kWpsWarps * kWarpFloats;
+  static constexpr int sm_tw = sm_img;                           // float4[16][32]
   static constexpr int sm_g = sm_tw + 2048;                      // float4[8][32]
   static constexpr int sm_wE = sm_g + 1024;                      // [kRH]      w[2q]
   static constexpr int sm_wO1 = sm_wE + kRH;                     // [kRH + 4]  w[2(q-1)+1], entry 0 = 0
-  static constexpr int sm_pw = sm_wO1 + kRH + 4;                 // [HOP + 1]  1 / (n_fft wss), entry HOP = entry 0
-  static constexpr int sm_total = sm_pw + (HOP + 4) / 4 * 4;
+  static constexpr int sm_pwx = sm_wO1 + kRH + 4;                // [kPwx]     pwx[j] = 1 / (n_fft wss[(j - 1) mod HOP])
+  static constexpr int image_floats = 2048 + 1024 + 2 * kRH + 4 + kPwx;
+  static constexpr int sm_mbar = sm_img + image_floats;          // 8-byte aligned (image_floats is a multiple of 4)
+  static constexpr int sm_total = sm_mbar + 4;
+  static constexpr bool kFits = sm_total * 4 <= 227 * 1024;
 };
 
 template <int SRC, bool SC, int HOP, int WIN>
@@ -86,10 +102,10 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
   const float4* const g4 = reinterpret_cast<const float4*>(smem + G::sm_g);
   const float* const wE = smem + G::sm_wE;
   const float* const wO1 = smem + G::sm_wO1;
-  const float* const pwn = smem + G::sm_pw;
+  const float* const pwx = smem + G::sm_pwx;
 
   // 1 / (n_fft * window sum of squares) at sample i of an utterance with T frames, over the frames that exist
-  // (librosa: divide only where wss > tiny); the interior uses the periodic table pwn instead
+  // (librosa: divide only where wss > tiny); the interior uses the periodic table pwx instead
   auto inv_wss = [&](int i, int T) {
     float ws = 0.0f;
     const int tq = (i + WIN / 2) / HOP;                            // last frame whose window starts at or before i
@@ -103,28 +119,29 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
     return ws > 1.17549435e-38f ? kInvN / ws : kInvN;
   };
 
-  // ---- prologue: tables and zeroed buffers (independent of the previous kernel's output)
-  for (int i = tid; i < kWpsWarps * G::kWarpFloats; i += kWpsThreads) smem[i] = 0.0f;
-  for (int i = tid; i < 512; i += kWpsThreads) reinterpret_cast<float4*>(smem + G::sm_tw)[i] = __ldg(tb.tw4 + i);
-  for (int i = tid; i < 256; i += kWpsThreads) reinterpret_cast<float4*>(smem + G::sm_g)[i] = __ldg(tb.g4 + i);
-  for (int i = tid; i < G::kRH; i += kWpsThreads) smem[G::sm_wE + i] = __ldg(tb.wE + i);
-  for (int i = tid; i < G::kRH + 4; i += kWpsThreads) smem[G::sm_wO1 + i] = i > 0 ? __ldg(tb.wO + i - 1) : 0.0f;
-  for (int i = tid; i <= HOP; i += kWpsThreads) smem[G::sm_pw + i] = __ldg(tb.pw + (i == HOP ? 0 : i)) * kInvN;
+  // ---- prologue (independent of the previous kernel's output): the table image by one bulk copy, this warp's range
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-  // this warp's range of the flattened frame list
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem + G::sm_mbar);
+  if (tid == 0) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem + G::sm_img);
+    constexpr unsigned bytes = (unsigned)G::image_floats * 4u;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(tb.wps_image), "r"(bytes), "r"(mbar) : "memory");
+  }
   const int wi = blockIdx.x * kWpsWarps + warp;
   const int fa = wp.cut[wi], fb = wp.cut[wi + 1];
-  int u = 0;
-  if (fa < fb) {
-    int lo = 0, hi = bd.B;                                         // largest u with tsum[u] <= fa
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (wp.tsum[mid] <= fa) lo = mid; else hi = mid;
+  int u = wp.u0[wi];                                               // utterance of frame fa (host-built)
+  __syncthreads();                                                 // the mbarrier is initialised for everyone
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                   : "=r"(done) : "r"(mbar) : "memory");
     }
-    u = lo;
   }
-  __syncthreads();
   // programmatic dependent launch: the previous kernel's waveform is complete from here on
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -163,9 +180,10 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       return span_to_smem_async_n<WIN + 2>(buf, src + a0, a.wav_in, a.wav_end, lane);
     };
     int x_off = 0;
-    if (span_fast(t_begin)) x_off = span_issue(t_begin);
+    if (span_fast(t_begin) && !(kProbe & 128)) x_off = span_issue(t_begin);
     int base = (((t_begin * HOP - WIN / 2) >> 1) + WIN) % G::kRH;  // ring slot of the first frame's first pair (a0 / 2, made positive)
 
+    int newq = 0;                                                  // first pair of the frame that no earlier frame of this run reached
 #pragma unroll 1
     for (int t = t_begin; t < t_end; ++t) {
       const int s0 = t * HOP - WIN / 2;
@@ -191,7 +209,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
           const float2* const xp = reinterpret_cast<const float2*>(buf + x_off) + lane;
 #pragma unroll
           for (int m = 0; m < 16; ++m) {
-            if (m < G::kMH) {
+            if (m < G::kMH && !(kProbe & 64)) {
               // pairs past the window hold stale exchange data: force zeros (their window taps are zero, but 0 * NaN of
               // another utterance's bad spectrum must not leak into this one)
               float2 xa = xp[64 * m];
@@ -209,7 +227,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             }
           }
           __syncwarp();                          // the landing zone becomes the exchange buffer
-        } else {
+        } else if (!(kProbe & 8)) {
           // ---------------------------------------------------------------- per-bin step -> conj(Z')   (as frame_kernel)
           float2 BR[8], BI[8];
           static_for<0, 8>([&](auto mc) {
@@ -298,10 +316,10 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
         // ------------------------------------------------------------------ 1024-point transform, 32 x 32
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
-          fft32p(R, I);
+          if (!(kProbe & 1)) fft32p(R, I);
           if (pass == 0) {
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {                        // times W_1024^(lane * k2), k2 = 2m, 2m+1
+            for (int m = 0; m < 16 && !(kProbe & 2); ++m) {       // times W_1024^(lane * k2), k2 = 2m, 2m+1
               const float4 w = tw4[m * 32 + lane];
               const float2 WR = make_float2(w.x, w.y), WI = make_float2(w.z, w.w);
               const float2 nr = __ffma2_rn(R[m], WR, neg2(__fmul2_rn(I[m], WI)));
@@ -310,7 +328,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             }
             __syncwarp();                                         // every lane is done with the buffer's previous contents
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {                        // row k2: [re 0..31 | im 0..31], column = lane
+            for (int m = 0; m < 16 && !(kProbe & 4); ++m) {       // row k2: [re 0..31 | im 0..31], column = lane
               buf[(2 * m) * kRowFloats + lane] = R[m].x;
               buf[(2 * m) * kRowFloats + 32 + lane] = I[m].x;
               buf[(2 * m + 1) * kRowFloats + lane] = R[m].y;
@@ -318,7 +336,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             }
             __syncwarp();
 #pragma unroll
-            for (int jq = 0; jq < 8; ++jq) {
+            for (int jq = 0; jq < 8 && !(kProbe & 4); ++jq) {
               const float4 qr = *reinterpret_cast<const float4*>(&buf[lane * kRowFloats + 4 * jq]);
               const float4 qi = *reinterpret_cast<const float4*>(&buf[lane * kRowFloats + 32 + 4 * jq]);
               R[2 * jq] = make_float2(qr.x, qr.y); R[2 * jq + 1] = make_float2(qr.z, qr.w);
@@ -327,7 +345,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             __syncwarp();
             // the exchange buffer is idle until the next exchange: land this frame's |S| row (forward half) or the
             // next frame's input span (inverse half) in it, so that their latency hides behind the coming pass
-            if (half == 0) {
+            if (kProbe & 128) {
+            } else if (half == 0) {
               s_off = span_to_smem_async_n<kF>(buf, spec_row0 + (long long)t * kF, a.spec, a.spec_end, lane);
             } else if (t + 1 < t_end && span_fast(t + 1)) {
               x_off = span_issue(t + 1);
@@ -336,82 +355,90 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
         }
       }  // halves
 
-      // -------------------------------------------------------------------- window, add into the ring
-      // element n2 = conj(z'[lane + 32 n2]): sample 2q = Re, sample 2q+1 = -Im
-      // (all ring loads first, then the arithmetic, then the stores: loads and stores of the same array cannot be
-      //  reordered by the compiler, and a load-modify-store chain per row would expose the shared-memory latency 18 times)
-      {
-        const int b0 = base + lane;
-        constexpr int kGroup = (G::kRows + 1) / 2;                 // two groups of rows: 2 x 9 accumulators in flight
-#pragma unroll
-        for (int n0 = 0; n0 < G::kRows; n0 += kGroup) {
-          float2 acc[kGroup];
-          int slot[kGroup];
-#pragma unroll
-          for (int j = 0; j < kGroup; ++j) {
-            if (n0 + j < G::kRows) {
-              int sl = b0 + 32 * (n0 + j); sl = sl >= G::kRH ? sl - G::kRH : sl;
-              slot[j] = sl;
-              acc[j] = ring[sl];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < kGroup; ++j) {
-            if (n0 + j < G::kRows) {
-              const int n = n0 + j;
-              const float yr = (n & 1) ? R[n >> 1].y : R[n >> 1].x, yi = (n & 1) ? I[n >> 1].y : I[n >> 1].x;
-              acc[j].x = fmaf(pe[32 * n], yr, acc[j].x);
-              acc[j].y = fmaf(-po[32 * n], yi, acc[j].y);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < kGroup; ++j)
-            if (n0 + j < G::kRows) ring[slot[j]] = acc[j];
-        }
-      }
-      __syncwarp();
-
-      // -------------------------------------------------------------------- finished samples leave the ring
+      // -------------------------------------------------------------------- window, overlap-add, emission: one pass
+      // element n2 = conj(z'[lane + 32 n2]): sample 2q = Re, sample 2q+1 = -Im.  Pair q of this frame lives in ring slot
+      // base + q.  Pairs q < count get their last term here and leave (* 1/(N wss) -> global, never stored back); pairs
+      // q >= newq were not reached by the previous frame and are stored without a load; the rest is load-add-store.
       const bool last = t == T - 1;                                // the utterance's last frame flushes the whole window
       const int pn = ((t + 1) * HOP - WIN / 2) & 1;
       const int count = last ? G::kNP : (HOP + p - pn) >> 1;       // pairs [a0/2, a0(t+1)/2)
-      const bool interior = !last && t >= G::kWarm && a0 >= zone_end && a0 >= 0 && a0 + 2 * count <= L;
-      if (interior) {
-        float2 v[G::kEmitIters], inv[G::kEmitIters];
-#pragma unroll
-        for (int it = 0; it < G::kEmitIters; ++it) {
-          const int e = lane + 32 * it;
-          int sl = base + e; sl = sl >= G::kRH ? sl - G::kRH : sl;
-          int r = 2 * e - p; r = r < 0 ? r + HOP : r; r = r >= HOP ? r - HOP : r;
-          v[it] = ring[sl];                                        // (e >= count reads a slot this frame did not finish: ignored)
-          inv[it] = make_float2(pwn[r], pwn[r + 1]);
-        }
-#pragma unroll
-        for (int it = 0; it < G::kEmitIters; ++it) {
-          const int e = lane + 32 * it;
-          if (e < count) {
-            int sl = base + e; sl = sl >= G::kRH ? sl - G::kRH : sl;
-            ring[sl] = make_float2(0.0f, 0.0f);
-            *reinterpret_cast<float2*>(dst + a0 + 2 * e) = make_float2(v[it].x * inv[it].x, v[it].y * inv[it].y);
+      const bool edge = last || t < G::kWarm || a0 < 0 || a0 + 2 * count > L;
+      const int b0 = base + lane;
+      // one row of 32 pairs; LOAD / EMIT: 0 = no lane, 1 = per lane (q < newq / q < count), 2 = every lane
+      auto row = [&](auto nc, auto loadc, float2& v, int& sl) {
+        constexpr int n = decltype(nc)::value, LOAD = decltype(loadc)::value;
+        sl = b0 + 32 * n; sl = sl >= G::kRH ? sl - G::kRH : sl;
+        v = make_float2(0.0f, 0.0f);
+        if (LOAD == 2 || (LOAD == 1 && lane + 32 * n < newq)) v = ring[sl];
+      };
+      auto finish_row = [&](auto nc, auto emitc, auto zonec, float2 v, int sl) {
+        constexpr int n = decltype(nc)::value, EMIT = decltype(emitc)::value;
+        constexpr bool ZONE = decltype(zonec)::value;
+        const float yr = (n & 1) ? R[n >> 1].y : R[n >> 1].x, yi = (n & 1) ? I[n >> 1].y : I[n >> 1].x;
+        v.x = fmaf(pe[32 * n], yr, v.x);
+        v.y = fmaf(-po[32 * n], yi, v.y);
+        if (EMIT == 0 || (kProbe & 32)) {
+          if (32 * n + 31 < G::kNP || lane + 32 * n < G::kNP) ring[sl] = v;
+        } else {
+          const int i = a0 + 2 * lane + 64 * n;                    // sample index of v.x
+          float2 sc2 = make_float2(pwx[2 * lane + 64 * n + 1 - p], pwx[2 * lane + 64 * n + 2 - p]);
+          if (ZONE) {                                              // raw partial sums inside the run's head zone
+            sc2.x = i < zone_end ? 1.0f : sc2.x;
+            sc2.y = i + 1 < zone_end ? 1.0f : sc2.y;
           }
+          if (EMIT == 2 || lane + 32 * n < count) *reinterpret_cast<float2*>(dst + i) = make_float2(v.x * sc2.x, v.y * sc2.y);
+          else ring[sl] = v;
         }
+      };
+      // rows in groups: all ring loads of a group first, then the arithmetic and the stores (loads and stores of the same
+      // array cannot be reordered by the compiler; a load-modify-store chain per row would expose the latency 18 times)
+      auto pass_rows = [&](auto zonec, auto edgec) {
+        constexpr bool ZONE = decltype(zonec)::value, EDGE = decltype(edgec)::value;
+        constexpr int kGroup = (G::kRows + 2) / 3;
+        static_for<0, 3>([&](auto gc) {
+          constexpr int n0 = decltype(gc)::value * kGroup;
+          float2 v[kGroup];
+          int sl[kGroup];
+          static_for<0, kGroup>([&](auto jc) {
+            constexpr int n = n0 + decltype(jc)::value;
+            if constexpr (n < G::kRows) {
+              // which lanes of this row still hold partial sums of earlier frames
+              constexpr int LOAD = (ZONE || EDGE) ? 1 : (32 * n + 31 < G::kNP - G::kCntMax ? 2 : (32 * n < G::kNP - G::kCntMin ? 1 : 0));
+              row(IntC<n>{}, IntC<LOAD>{}, v[decltype(jc)::value], sl[decltype(jc)::value]);
+            }
+          });
+          static_for<0, kGroup>([&](auto jc) {
+            constexpr int n = n0 + decltype(jc)::value;
+            if constexpr (n < G::kRows) {
+              constexpr int EMIT = EDGE ? 0 : (32 * n + 31 < G::kCntMin ? 2 : (32 * n < G::kCntMax ? 1 : 0));
+              finish_row(IntC<n>{}, IntC<EMIT>{}, zonec, v[decltype(jc)::value], sl[decltype(jc)::value]);
+            }
+          });
+        });
+      };
+      if (kProbe & 16) {
+      } else if (!edge) {
+        if (a0 >= zone_end && newq > 0) pass_rows(IntC<0>{}, IntC<0>{});   // steady state
+        else pass_rows(IntC<1>{}, IntC<0>{});                              // head zone of a run / its first frame
       } else {
+        // utterance edges (first kWarm frames, last frame): everything goes through the ring, then a slow emission with
+        // the window sum over the frames that exist
+        pass_rows(IntC<0>{}, IntC<1>{});
+        __syncwarp();
 #pragma unroll 1
-        for (int e = lane; e < (last ? G::kRH : count); e += 32) { // the last frame leaves the whole ring zero
+        for (int e = lane; e < count && !(kProbe & 32); e += 32) {
           int sl = base + e; sl = sl >= G::kRH ? sl - G::kRH : sl;
           const float2 v = ring[sl];
-          ring[sl] = make_float2(0.0f, 0.0f);
-          if (e < count) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int i = a0 + 2 * e + h;
-              const float val = h ? v.y : v.x;
-              if (i >= 0 && i < L) dst[i] = i < zone_end ? val : val * inv_wss(i, T);   // raw partial sum inside the head zone
-            }
+          for (int h = 0; h < 2; ++h) {
+            const int i = a0 + 2 * e + h;
+            const float val = h ? v.y : v.x;
+            if (i >= 0 && i < L) dst[i] = i < zone_end ? val : val * inv_wss(i, T);   // raw partial sum inside the head zone
           }
         }
       }
       __syncwarp();
+      newq = G::kNP - count;
       base += count; base = base >= G::kRH ? base - G::kRH : base;
       if (zone_pending && a0 + 2 * count >= zone_end) {            // the head zone is stored: the owner of the frames before
         __threadfence();                                           // the cut may finish it (release at gpu scope)
@@ -465,8 +492,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
           float2 r2 = o[k];
           if (all_frames) {
             int r = (i - s0z) % HOP; r = r < 0 ? r + HOP : r;
-            r2.x = (o[k].x + v[k].x) * pwn[r];
-            if (i + 1 < zend) r2.y = (o[k].y + v[k].y) * pwn[r + 1];
+            r2.x = (o[k].x + v[k].x) * pwx[r + 1];
+            if (i + 1 < zend) r2.y = (o[k].y + v[k].y) * pwx[r + 2];
           } else {
             r2.x = (o[k].x + v[k].x) * inv_wss(i, T);
             if (i + 1 < zend && i + 1 < L) r2.y = (o[k].y + v[k].y) * inv_wss(i + 1, T);

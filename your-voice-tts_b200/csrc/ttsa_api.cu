@@ -96,8 +96,8 @@ struct ttsa_batch {
   // warp-stream Griffin-Lim partition: one contiguous range of the flattened frame list per warp of a 16-warp CTA per SM
   bool wps_ok = false;
   int wps_grid = 0, wps_win = 0;
-  std::vector<int> wps_cut, tsum;
-  WpsDev wps_dev{nullptr, nullptr};
+  std::vector<int> wps_cut, tsum, wps_u0;
+  WpsDev wps_dev{nullptr, nullptr, nullptr};
   void* d_block = nullptr;
   BatchDev dev;
   const int* d_chunk_off = nullptr;
@@ -398,6 +398,23 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     h_pw2[2 * r] = h_pw[r] * (1.0f / (float)kNfft);
     h_pw2[2 * r + 1] = h_pw[(r + 1) % c.hop_length] * (1.0f / (float)kNfft);
   }
+  // table image of the warp-stream Griffin-Lim kernel (gl_stream.cuh, WpsGeo<hop, win>): tw4 | g4 | wE | wO1 | pwx
+  std::vector<float> h_wps;
+  {
+    const int np = c.win_length / 2 + (c.hop_length & 1), rh = (np + 31) / 32 * 32;
+    const int emit_rows = ((c.hop_length + 1) / 2 + 31) / 32, npwx = (64 * emit_rows + 4 + 3) / 4 * 4;
+    h_wps.assign(2048 + 1024 + 2 * (size_t)rh + 4 + npwx, 0.f);
+    float* q = h_wps.data();
+    for (int i = 0; i < 2048; ++i) q[i] = h_tw[i];
+    q += 2048;
+    for (int i = 0; i < 1024; ++i) q[i] = h_g[i];
+    q += 1024;
+    for (int i = 0; i < rh && i < 1024; ++i) q[i] = h_wE[i];
+    q += rh;
+    for (int i = 1; i < rh + 4 && i - 1 < 1024; ++i) q[i] = h_wO[i - 1];          // entry 0 = 0: the tap before the window
+    q += rh + 4;
+    for (int j = 0; j < npwx; ++j) q[j] = h_pw[(j - 1 + c.hop_length) % c.hop_length] * (1.0f / (float)kNfft);
+  }
   // shared-memory image of the frame kernels' constant tables (Layout: [sm_wE, sm_mbar))
   const Layout& ly = p->geo.ly;
   std::vector<float> h_img(ly.image_floats, 0.f);
@@ -460,7 +477,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       {h_wE2.data(), h_wE2.size() * 4, 0}, {h_wO2.data(), h_wO2.size() * 4, 0},
       {h_pinv_tc.data(), h_pinv_tc.size() * 2, 0}, {h_mel_tc.data(), h_mel_tc.size() * 2, 0},
       {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}, {h_img.data(), h_img.size() * 4, 0},
-      {h_melc.data(), h_melc.size() * 4, 0}, {h_pw2.data(), h_pw2.size() * 4, 0}};
+      {h_melc.data(), h_melc.size() * 4, 0}, {h_pw2.data(), h_pw2.size() * 4, 0}, {h_wps.data(), h_wps.size() * 4, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -485,6 +502,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->tb.wO = (const float*)(base + pieces[3].off);
   p->tb.pw = (const float*)(base + pieces[4].off);
   p->tb.pw2 = (const float2*)(base + pieces[16].off);
+  p->tb.wps_image = (const float*)(base + pieces[17].off);
   p->tb.mel_lo = (const int*)(base + pieces[5].off);
   p->tb.mel_cnt = (const int*)(base + pieces[6].off);
   p->tb.mel_val = (const float*)(base + pieces[7].off);
@@ -561,7 +579,7 @@ static bool build_wps_partition(const std::vector<int>& T, int hop, int win, int
     tsum[u + 1] = (int)total;
   }
   const int G = (int)total;
-  const int nw = grid * 16;
+  const int nw = grid * kWpsWarps;
   if (grid <= 0 || (long long)G < (long long)nw * (2 * minrun)) return false;
   cut.assign(nw + 1, 0);
   for (int i = 0; i <= nw; ++i) cut[i] = (int)((long long)i * G / nw);
@@ -636,11 +654,20 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
     b->wps_grid = plan->wps_grid;
     b->wps_win = plan->cfg.win_length;
     b->wps_ok = build_wps_partition(b->T, b->hop, b->wps_win, b->wps_grid, b->tsum, b->wps_cut);
+    if (b->wps_ok) {                                       // utterance that holds the first frame of each warp's range
+      const int nw = (int)b->wps_cut.size() - 1;
+      b->wps_u0.assign(nw, 0);
+      int u = 0;
+      for (int i = 0; i < nw; ++i) {
+        while (u + 1 < B && b->tsum[u + 1] <= b->wps_cut[i]) ++u;
+        b->wps_u0[i] = u;
+      }
+    }
   }
   if (plan->device >= 0) {
     DeviceGuard guard(plan->device);
-    const size_t n_wps = b->wps_ok ? b->tsum.size() + b->wps_cut.size() : 0;
-    const size_t n_i = (size_t)B * 2 + (size_t)(B + 1) * 2 + n_wps;     // T, wav_len, tile_off, chunk_off, [tsum, wps_cut]
+    const size_t n_wps = b->wps_ok ? b->tsum.size() + b->wps_cut.size() + b->wps_u0.size() : 0;
+    const size_t n_i = (size_t)B * 2 + (size_t)(B + 1) * 2 + n_wps;     // T, wav_len, tile_off, chunk_off, [tsum, wps_cut, wps_u0]
     const size_t bytes_i = (n_i * 4 + 15) / 16 * 16;
     const size_t bytes_l = (size_t)(B + 1) * 2 * 8;
     if (cudaMalloc(&b->d_block, bytes_i + bytes_l) != cudaSuccess) { delete b; return fail(TTSA_ERR_CUDA, "cudaMalloc for batch layout failed"); }
@@ -656,6 +683,7 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
     if (b->wps_ok) {
       std::memcpy(hi + 2 * B + 2 * (B + 1), b->tsum.data(), b->tsum.size() * 4);
       std::memcpy(hi + 2 * B + 3 * (B + 1), b->wps_cut.data(), b->wps_cut.size() * 4);
+      std::memcpy(hi + 2 * B + 3 * (B + 1) + b->wps_cut.size(), b->wps_u0.data(), b->wps_u0.size() * 4);
     }
     cudaError_t e = cudaMemcpy(b->d_block, h.data(), h.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(b->d_block); delete b; return fail(TTSA_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e)); }
@@ -667,7 +695,11 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
     b->dev.wav_len = di + B;
     b->dev.tile_off = di + 2 * B;
     b->d_chunk_off = di + 2 * B + (B + 1);
-    if (b->wps_ok) { b->wps_dev.tsum = di + 2 * B + 2 * (B + 1); b->wps_dev.cut = di + 2 * B + 3 * (B + 1); }
+    if (b->wps_ok) {
+      b->wps_dev.tsum = di + 2 * B + 2 * (B + 1);
+      b->wps_dev.cut = di + 2 * B + 3 * (B + 1);
+      b->wps_dev.u0 = b->wps_dev.cut + b->wps_cut.size();
+    }
   }
   *out = b;
   return TTSA_OK;
@@ -794,7 +826,7 @@ extern "C" size_t ttsa_deemphasis_workspace_bytes(const ttsa_plan* plan, const t
 }
 
 static size_t wps_flag_bytes(const ttsa_batch* batch) {
-  return batch->wps_ok ? ((size_t)batch->wps_grid * 16 * 4 + 255) / 256 * 256 : 0;
+  return batch->wps_ok ? ((size_t)batch->wps_grid * kWpsWarps * 4 + 255) / 256 * 256 : 0;
 }
 
 extern "C" size_t ttsa_griffin_lim_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* batch) {
