@@ -83,6 +83,8 @@ struct Tables {
   const float* wO;       // [1024]    w[2q+1]
   const float* pw;       // [hop]    1 / sum_q w[r + q*hop]^2   (interior window-sum-square, periodic in hop)
   const float2* pw2;     // [hop]    (pw[r], pw[(r + 1) % hop]) / n_fft   (sample pairs of the warp-stream Griffin-Lim kernel)
+  const float* edge_head;   // [max(0, warm*hop - win/2)]  1 / (n_fft wss) of an utterance's first samples (frames before 0 missing)
+  const float* edge_tail;   // [max(0, win/2 - hop)]       the same for its last samples (frame T missing); gl_stream.cuh
   const float* wps_image;   // table image of the warp-stream Griffin-Lim kernel (gl_stream.cuh, WpsGeo): tw4 | g4 | wE | wO1 | pwx
   const float* smem_image;  // [Layout::image_floats]  wE2 | wO2 | pw / n_fft | signed synthesis window | tw4 | g4, laid out
                             // exactly as the kernels keep them in shared memory (one bulk copy per CTA)

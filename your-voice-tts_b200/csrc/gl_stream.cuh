@@ -70,6 +70,11 @@ struct WpsGeo {
   static_assert(kRows <= 20, "window too long for this kernel");
   static constexpr int kCntMin = HOP / 2, kCntMax = (HOP + 1) / 2;   // pairs that leave the ring per interior frame
   static constexpr int kEmitRows = (kCntMax + 31) / 32;
+  // utterance edges: samples [0, kHead) lack frames before the first one, the last kTail samples the frame after the
+  // last one; their 1 / (n_fft wss) comes from two plan tables when the utterance is long enough for both to be exact
+  static constexpr int kHead = kWarm * HOP - WIN / 2 > 0 ? kWarm * HOP - WIN / 2 : 0;
+  static constexpr int kTail = WIN / 2 - HOP > 0 ? WIN / 2 - HOP : 0;
+  static constexpr int kEdgeMinT = 2 * kWarm + 2;
   static constexpr int kPwx = (64 * kEmitRows + 4 + 3) / 4 * 4;  // entries of the shifted 1/(N wss) table
   static_assert(kPwx >= HOP + 2, "hop too long for the emission table");
   // shared memory (floats): per-warp buffers, then the constant tables as ONE host-built image (Tables::wps_image)
@@ -117,6 +122,13 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       }
     }
     return ws > 1.17549435e-38f ? kInvN / ws : kInvN;
+  };
+  // the same through the plan's edge tables (Tables::edge_head / edge_tail) and the periodic table
+  auto edge_inv = [&](int i, int T, int L) {
+    if (T < G::kEdgeMinT) return inv_wss(i, T);
+    if (i < G::kHead) return __ldg(tb.edge_head + i);
+    if (i >= L - G::kTail) return __ldg(tb.edge_tail + (i - (L - G::kTail)));
+    return pwx[(i + WIN / 2) % HOP + 1];
   };
 
   // ---- prologue (independent of the previous kernel's output): the table image by one bulk copy, this warp's range
@@ -177,10 +189,14 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
     auto span_issue = [&](int t) {                                 // returns the landing offset (0 or 2)
       const int s0 = t * HOP - WIN / 2;
       const int a0 = s0 - (s0 & 1);
-      return span_to_smem_async_n<WIN + 2>(buf, src + a0, a.wav_in, a.wav_end, lane);
+      if (span_fast(t)) return span_to_smem_async_n<WIN + 2>(buf, src + a0, a.wav_in, a.wav_end, lane);
+      // the utterance's first and last frames: np.pad(..., mode='reflect') as an index map, 4-byte asynchronous copies
+#pragma unroll 4
+      for (int m = lane; m < WIN + 2; m += 32) cp_async4(buf + m, src + reflect_index(a0 + m, L));
+      return 0;
     };
     int x_off = 0;
-    if (span_fast(t_begin) && !(kProbe & 128)) x_off = span_issue(t_begin);
+    if (!(kProbe & 128)) x_off = span_issue(t_begin);
     int base = (((t_begin * HOP - WIN / 2) >> 1) + WIN) % G::kRH;  // ring slot of the first frame's first pair (a0 / 2, made positive)
 
     int newq = 0;                                                  // first pair of the frame that no earlier frame of this run reached
@@ -198,13 +214,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       for (int half = 0; half < 2; ++half) {
         if (half == 0) {
           // ---------------------------------------------------------------- input span -> windowed packed frame
-          if (span_fast(t)) {
-            cp_async_wait_all();
-          } else {
-            __syncwarp();
-            for (int m = lane; m < WIN + 2; m += 32) buf[m] = __ldg(src + reflect_index(a0 + m, L));
-            x_off = 0;
-          }
+          cp_async_wait_all();
           __syncwarp();
           const float2* const xp = reinterpret_cast<const float2*>(buf + x_off) + lane;
 #pragma unroll
@@ -348,7 +358,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             if (kProbe & 128) {
             } else if (half == 0) {
               s_off = span_to_smem_async_n<kF>(buf, spec_row0 + (long long)t * kF, a.spec, a.spec_end, lane);
-            } else if (t + 1 < t_end && span_fast(t + 1)) {
+            } else if (t + 1 < t_end) {
               x_off = span_issue(t + 1);
             }
           }
@@ -433,7 +443,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
           for (int h = 0; h < 2; ++h) {
             const int i = a0 + 2 * e + h;
             const float val = h ? v.y : v.x;
-            if (i >= 0 && i < L) dst[i] = i < zone_end ? val : val * inv_wss(i, T);   // raw partial sum inside the head zone
+            if (i >= 0 && i < L) dst[i] = i < zone_end ? val : val * edge_inv(i, T, L);   // raw partial sum inside the head zone
           }
         }
       }
@@ -495,8 +505,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             r2.x = (o[k].x + v[k].x) * pwx[r + 1];
             if (i + 1 < zend) r2.y = (o[k].y + v[k].y) * pwx[r + 2];
           } else {
-            r2.x = (o[k].x + v[k].x) * inv_wss(i, T);
-            if (i + 1 < zend && i + 1 < L) r2.y = (o[k].y + v[k].y) * inv_wss(i + 1, T);
+            r2.x = (o[k].x + v[k].x) * edge_inv(i, T, L);
+            if (i + 1 < zend && i + 1 < L) r2.y = (o[k].y + v[k].y) * edge_inv(i + 1, T, L);
           }
           *reinterpret_cast<float2*>(dst + i) = r2;
         }

@@ -398,6 +398,28 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     h_pw2[2 * r] = h_pw[r] * (1.0f / (float)kNfft);
     h_pw2[2 * r + 1] = h_pw[(r + 1) % c.hop_length] * (1.0f / (float)kNfft);
   }
+  // 1 / (n_fft * window sum of squares) at the edges of an utterance (gl_stream.cuh): sample i < warm*hop - win/2 lacks the
+  // frames before frame 0, sample L - ntail + j lacks frame T (the frames are at t*hop - win/2, L = hop*(T-1))
+  std::vector<float> h_edge_head, h_edge_tail;
+  {
+    const int hop = c.hop_length, win = c.win_length, warm = (win - 1) / hop;
+    const int nhead = std::max(0, warm * hop - win / 2), ntail = std::max(0, win / 2 - hop);
+    h_edge_head.assign(std::max(nhead, 1), 0.f);
+    h_edge_tail.assign(std::max(ntail, 1), 0.f);
+    // the kernel adds the terms from the latest frame down (same order here: bit-identical to its on-the-fly sum)
+    auto inv_wss_desc = [&](long long i, long long t_lo, long long t_hi) {   // frames t_lo..t_hi exist
+      float ws = 0.f;
+      for (long long tt = t_hi; tt >= t_lo; --tt) {
+        const long long m = i - (tt * hop - win / 2);
+        if (m >= 0 && m < win) { const float wf = (float)w[m]; ws = std::fmaf(wf, wf, ws); }
+      }
+      return ws > 1.17549435e-38f ? (1.0f / (float)kNfft) / ws : 1.0f / (float)kNfft;
+    };
+    const long long Tbig = 1000;                                        // any utterance long enough for both tables
+    for (int i = 0; i < nhead; ++i) h_edge_head[i] = inv_wss_desc(i, 0, Tbig - 1);
+    const long long Lbig = (long long)hop * (Tbig - 1);
+    for (int j = 0; j < ntail; ++j) h_edge_tail[j] = inv_wss_desc(Lbig - ntail + j, 0, Tbig - 1);
+  }
   // table image of the warp-stream Griffin-Lim kernel (gl_stream.cuh, WpsGeo<hop, win>): tw4 | g4 | wE | wO1 | pwx
   std::vector<float> h_wps;
   {
@@ -477,7 +499,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       {h_wE2.data(), h_wE2.size() * 4, 0}, {h_wO2.data(), h_wO2.size() * 4, 0},
       {h_pinv_tc.data(), h_pinv_tc.size() * 2, 0}, {h_mel_tc.data(), h_mel_tc.size() * 2, 0},
       {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}, {h_img.data(), h_img.size() * 4, 0},
-      {h_melc.data(), h_melc.size() * 4, 0}, {h_pw2.data(), h_pw2.size() * 4, 0}, {h_wps.data(), h_wps.size() * 4, 0}};
+      {h_melc.data(), h_melc.size() * 4, 0}, {h_pw2.data(), h_pw2.size() * 4, 0}, {h_wps.data(), h_wps.size() * 4, 0},
+      {h_edge_head.data(), h_edge_head.size() * 4, 0}, {h_edge_tail.data(), h_edge_tail.size() * 4, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -503,6 +526,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->tb.pw = (const float*)(base + pieces[4].off);
   p->tb.pw2 = (const float2*)(base + pieces[16].off);
   p->tb.wps_image = (const float*)(base + pieces[17].off);
+  p->tb.edge_head = (const float*)(base + pieces[18].off);
+  p->tb.edge_tail = (const float*)(base + pieces[19].off);
   p->tb.mel_lo = (const int*)(base + pieces[5].off);
   p->tb.mel_cnt = (const int*)(base + pieces[6].off);
   p->tb.mel_val = (const float*)(base + pieces[7].off);
