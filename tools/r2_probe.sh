@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for v in "" _p255 _p127 _p48 _p8 _p1; do
+for v in "" _p1 _p2 _p4 _p8 _p16 _p64 _p128 _p255; do
   TTSA_DEBUG=0 TTSA_LIB=$PWD/your-voice-tts_b200/libttsa_b200$v.so python bench.py --no-cpu-baseline --steps 3 2>/dev/null | tail -1 | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('variant[$v] iter_ms', round(d['roofline']['launch_ms'],4), 'step', round(d['ms_per_step'],3))"
 done 2>&1 | tee gpurun_out/r2_probe.log

@@ -55,6 +55,37 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 #endif
 constexpr int kProbe = TTSA_PROBE;
 
+// One row of the spectrogram / one input span into the warp's buffer by ONE bulk asynchronous copy (the enclosing
+// 16-byte-aligned range; completion on the warp's mbarrier) instead of nine 16-byte cp.async per lane: no address
+// arithmetic, no load/store-unit wavefronts, one issuing lane.  Ranges that would leave the tensor fall back to cp.async.
+// Returns the landing offset of element 0 (0..3); `bulk` tells which completion mechanism to wait on.
+template <int N>
+__device__ __forceinline__ int span_to_smem_bulk_n(float* dst, const float* ptr, const float* lo, const float* hi, int lane,
+                                                   unsigned mbar, bool& bulk) {
+  const int off = (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ull);
+  const float* base = ptr - off;                      // 16-byte aligned
+  constexpr int kMaxChunks = (3 + N + 3) >> 2;
+  bulk = base >= lo && base + 4 * kMaxChunks <= hi;
+  if (bulk) {
+    if (lane == 0) {
+      const unsigned bytes = (unsigned)((off + N + 3) >> 2) << 4;
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(d), "l"(base), "r"(bytes), "r"(mbar) : "memory");
+    }
+    return off;
+  }
+  return span_to_smem_async(dst, ptr, N, lo, hi, lane);
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  }
+}
+
 template <int HOP, int WIN>
 struct WpsGeo {
   static_assert(WIN % 2 == 0 && HOP >= 2 && WIN >= HOP, "even window not shorter than the hop");
@@ -87,7 +118,7 @@ struct WpsGeo {
   static constexpr int sm_pwx = sm_wO1 + kRH + 4;                // [kPwx]     pwx[j] = 1 / (n_fft wss[(j - 1) mod HOP])
   static constexpr int image_floats = 2048 + 1024 + 2 * kRH + 4 + kPwx;
   static constexpr int sm_mbar = sm_img + image_floats;          // 8-byte aligned (image_floats is a multiple of 4)
-  static constexpr int sm_total = sm_mbar + 4;
+  static constexpr int sm_total = sm_mbar + 4 + 4 * kWpsWarps;   // + two mbarriers per warp (|S| row, input span)
   static constexpr bool kFits = sm_total * 4 <= 227 * 1024;
 };
 
@@ -138,6 +169,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem + G::sm_img);
     constexpr unsigned bytes = (unsigned)G::image_floats * 4u;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    for (int i = 0; i < 2 * kWpsWarps; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar + 16 + 8 * i) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -157,6 +189,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
   // programmatic dependent launch: the previous kernel's waveform is complete from here on
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
+  const unsigned mbar_s = mbar + 16 + 16 * warp, mbar_x = mbar_s + 8;   // this warp's copy barriers and their phases
+  unsigned ph_s = 0, ph_x = 0;
   const int partner = (32 - lane) & 31;
   const bool l0 = lane == 0;
   int f = fa;
@@ -186,10 +220,12 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       const int a0 = s0 - (s0 & 1);
       return a0 >= 0 && a0 + WIN + 2 <= L;
     };
+    bool x_bulk = false;
     auto span_issue = [&](int t) {                                 // returns the landing offset (0 or 2)
       const int s0 = t * HOP - WIN / 2;
       const int a0 = s0 - (s0 & 1);
-      if (span_fast(t)) return span_to_smem_async_n<WIN + 2>(buf, src + a0, a.wav_in, a.wav_end, lane);
+      if (span_fast(t)) return span_to_smem_bulk_n<WIN + 2>(buf, src + a0, a.wav_in, a.wav_end, lane, mbar_x, x_bulk);
+      x_bulk = false;
       // the utterance's first and last frames: np.pad(..., mode='reflect') as an index map, 4-byte asynchronous copies
 #pragma unroll 4
       for (int m = lane; m < WIN + 2; m += 32) cp_async4(buf + m, src + reflect_index(a0 + m, L));
@@ -197,6 +233,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
     };
     int x_off = 0;
     if (!(kProbe & 128)) x_off = span_issue(t_begin);
+    bool s_bulk = false;
     int base = (((t_begin * HOP - WIN / 2) >> 1) + WIN) % G::kRH;  // ring slot of the first frame's first pair (a0 / 2, made positive)
 
     int newq = 0;                                                  // first pair of the frame that no earlier frame of this run reached
@@ -214,7 +251,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       for (int half = 0; half < 2; ++half) {
         if (half == 0) {
           // ---------------------------------------------------------------- input span -> windowed packed frame
-          cp_async_wait_all();
+          if (x_bulk) { mbar_wait(mbar_x, ph_x); ph_x ^= 1u; x_bulk = false; }
+          else cp_async_wait_all();
           __syncwarp();
           const float2* const xp = reinterpret_cast<const float2*>(buf + x_off) + lane;
 #pragma unroll
@@ -248,7 +286,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             BR[m] = shfl2(s0r, s1r, partner);
             BI[m] = shfl2(s0i, s1i, partner);
           });
-          cp_async_wait_all();                   // this frame's |S| row (issued between the two forward passes)
+          if (s_bulk) { mbar_wait(mbar_s, ph_s); ph_s ^= 1u; }   // this frame's |S| row (issued between the two forward passes)
+          else cp_async_wait_all();
           __syncwarp();
           const float* srow = buf + s_off;
           float2 SR[8], SI[8];
@@ -355,9 +394,9 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             __syncwarp();
             // the exchange buffer is idle until the next exchange: land this frame's |S| row (forward half) or the
             // next frame's input span (inverse half) in it, so that their latency hides behind the coming pass
-            if (kProbe & 128) {
+            if ((kProbe & 128) || ((kProbe & 8) && half == 0)) {
             } else if (half == 0) {
-              s_off = span_to_smem_async_n<kF>(buf, spec_row0 + (long long)t * kF, a.spec, a.spec_end, lane);
+              s_off = span_to_smem_bulk_n<kF>(buf, spec_row0 + (long long)t * kF, a.spec, a.spec_end, lane, mbar_s, s_bulk);
             } else if (t + 1 < t_end) {
               x_off = span_issue(t + 1);
             }
