@@ -224,7 +224,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
     auto span_issue = [&](int t) {                                 // returns the landing offset (0 or 2)
       const int s0 = t * HOP - WIN / 2;
       const int a0 = s0 - (s0 & 1);
-      if (span_fast(t)) return span_to_smem_bulk_n<WIN + 2>(buf, src + a0, a.wav_in, a.wav_end, lane, mbar_x, x_bulk);
+      if (span_fast(t)) return span_to_smem_bulk_n<WIN + 2>(buf, (kProbe & 4096) ? src + 4096 + (a0 & 2) + 64 * warp : src + a0, a.wav_in, a.wav_end, lane, mbar_x, x_bulk);
       x_bulk = false;
       // the utterance's first and last frames: np.pad(..., mode='reflect') as an index map, 4-byte asynchronous copies
 #pragma unroll 4
@@ -232,7 +232,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       return 0;
     };
     int x_off = 0;
-    if (!(kProbe & 128)) x_off = span_issue(t_begin);
+    if (!(kProbe & (128 | 1024))) x_off = span_issue(t_begin);
     bool s_bulk = false;
     int base = (((t_begin * HOP - WIN / 2) >> 1) + WIN) % G::kRH;  // ring slot of the first frame's first pair (a0 / 2, made positive)
 
@@ -245,13 +245,25 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       const float* const pe = p ? wO1 + lane : wE + lane;          // window of the even / odd sample of pair q = lane + 32 n2
       const float* const po = p ? wE + lane : wO1 + 1 + lane;
 
+      // pull the next frame's |S| row and the input span after next towards L2 (their copies are issued later in this
+      // frame / in the next one and would otherwise pay the full HBM latency inside one transform pass)
+      if (!(kProbe & 256)) {
+        const char* nrow = reinterpret_cast<const char*>(spec_row0 + (long long)(t + 1) * kF) + 128 * lane;
+        if (t + 1 < t_end && nrow + 128 <= reinterpret_cast<const char*>(a.spec_end)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
+        const char* nspan = reinterpret_cast<const char*>(src + a0 + 2 * HOP) + 128 * lane;
+        if (t + 2 < t_end && nspan + 1024 + 128 <= reinterpret_cast<const char*>(a.wav_end)) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nspan));
+          if (lane < (4 * (WIN + 2) + 127) / 128 - 32 + 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(nspan + 4096));
+        }
+      }
       float2 R[16], I[16];
       int s_off = 0;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         if (half == 0) {
           // ---------------------------------------------------------------- input span -> windowed packed frame
-          if (x_bulk) { mbar_wait(mbar_x, ph_x); ph_x ^= 1u; x_bulk = false; }
+          if (kProbe & 2048) {
+          } else if (x_bulk) { mbar_wait(mbar_x, ph_x); ph_x ^= 1u; x_bulk = false; }
           else cp_async_wait_all();
           __syncwarp();
           const float2* const xp = reinterpret_cast<const float2*>(buf + x_off) + lane;
@@ -286,7 +298,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             BR[m] = shfl2(s0r, s1r, partner);
             BI[m] = shfl2(s0i, s1i, partner);
           });
-          if (s_bulk) { mbar_wait(mbar_s, ph_s); ph_s ^= 1u; }   // this frame's |S| row (issued between the two forward passes)
+          if (kProbe & 2048) {
+          } else if (s_bulk) { mbar_wait(mbar_s, ph_s); ph_s ^= 1u; }   // this frame's |S| row (issued between the two forward passes)
           else cp_async_wait_all();
           __syncwarp();
           const float* srow = buf + s_off;
@@ -394,7 +407,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             __syncwarp();
             // the exchange buffer is idle until the next exchange: land this frame's |S| row (forward half) or the
             // next frame's input span (inverse half) in it, so that their latency hides behind the coming pass
-            if ((kProbe & 128) || ((kProbe & 8) && half == 0)) {
+            if ((kProbe & 128) || ((kProbe & 8) && half == 0) || ((kProbe & 512) && half == 0) || ((kProbe & 1024) && half == 1)) {
             } else if (half == 0) {
               s_off = span_to_smem_bulk_n<kF>(buf, spec_row0 + (long long)t * kF, a.spec, a.spec_end, lane, mbar_s, s_bulk);
             } else if (t + 1 < t_end) {
