@@ -11,7 +11,10 @@ mel basis -> 60 Griffin-Lim iterations -> de-emphasis -- over 64 synthetic 6 s u
   e2e     same metric through the public AudioProcessor call with HOST buffers: pinned host mel -> device,
           compute, device -> pinned host waveform, all inside the timed region
   roofline  Griffin-Lim iteration kernel: algorithmic bytes per launch / measured launch duration vs the measured
-          HBM copy bandwidth (MEASURED_PEAKS.json)
+          HBM copy bandwidth (MEASURED_PEAKS.json); roofline_fp32: the FP32 pipe, the roof that actually binds
+  e2e_dropin  the same 64 utterances through the reference-signature call, one ap.inv_mel_spectrogram(np.ndarray)
+          per utterance, host arrays in and out, host-drawn random phases as the reference
+  latency_single_ms  BASELINE configs[0]: one 6 s linear spectrogram through inv_spectrogram, device resident
   cpu_baseline  the float64 oracle port of the reference (oracle/audio_oracle.py) on the host cores, bounded sample
 
 --impl reference runs that CPU implementation alone (rank 0 only) and prints the same line.
@@ -200,7 +203,7 @@ def run_reference(args, rank):
     total = args.warmup + args.steps
     # every step is a bounded sample (one utterance per host thread, ~3-5 s of wall time); the requested step counts
     # are honoured up to a bound that keeps the whole run within a few minutes
-    n_warm, n_steps = min(args.warmup, 2), max(1, min(args.steps, 30))
+    n_warm, n_steps = max(0, args.warmup), max(1, min(args.steps, 30))
     for i in range(n_warm + n_steps):
         v, dt = cpu_reference_run(per_step, cores)
         if i >= n_warm:
@@ -210,7 +213,9 @@ def run_reference(args, rank):
     sample = "%d utterances (one per host thread) x inv_mel_spectrogram %d iters per step, %d of %d requested steps" % (
         per_step, ITERS, n_steps, args.steps)
     line = {"impl": "reference", "metric": "griffin_lim_audio_sec_per_sec", "value": value, "unit": "audio-s/s",
-            "n_gpus": args.gpus, "steps": n_steps, "warmup": n_warm, "ms_per_step": ms, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": n_steps, "warmup": n_warm, "steps_requested": args.steps,
+            "warmup_requested": args.warmup, "steps_clamped": n_steps != args.steps,
+            "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, 64),
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
@@ -220,8 +225,9 @@ def run_reference(args, rank):
 
 
 def config_dict(args, batch):
-    return {"workload": "configs[1]: batched inv_mel_spectrogram, 80 mels -> pinv mel basis -> Griffin-Lim %d iters "
-                        "-> de-emphasis, %d synthetic 6 s utterances per GPU" % (ITERS, batch),
+    which = "configs[1]" if (batch == 64 and ITERS == 60) else "configs[4] shard (throughput sweep)"
+    return {"workload": "%s: batched inv_mel_spectrogram, 80 mels -> pinv mel basis -> Griffin-Lim %d iters "
+                        "-> de-emphasis, %d synthetic 6 s utterances per GPU" % (which, ITERS, batch),
             "sample_rate": SR, "num_freq": F, "n_fft": 2048, "hop_length": HOP, "win_length": 1102,
             "frames_per_utt": T_FRAMES, "utts_per_gpu": batch, "griffin_lim_iters": ITERS,
             "parallelism": "utterances sharded across GPUs, no data-path collective",
@@ -238,6 +244,8 @@ def main():
     ap_.add_argument("--iters", type=int, default=ITERS, help="Griffin-Lim iterations (BASELINE configs[4] sweeps 30 and 60)")
     ap_.add_argument("--no-cpu-baseline", action="store_true")
     ap_.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
+    ap_.add_argument("--gather", action="store_true", help="also time the optional final gather of the waveforms (NCCL)")
+    ap_.add_argument("--no-extras", action="store_true", help="skip e2e_dropin / latency_single_ms (profiling runs)")
     args = ap_.parse_args()
     globals()["ITERS"] = int(args.iters)
     AUDIO["griffin_lim_iters"] = int(args.iters)
@@ -390,19 +398,39 @@ def main():
     hbm_peak, peak_src = peaks()
     algo_bytes = B * BYTES_PER_UTT_ITER
     achieved = algo_bytes / (iter_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, prof = None, {}
     tpath = os.path.join(ROOT, "profiles", "gl_iter_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            prof = json.load(open(tpath))
+            traffic = prof.get("dram_bytes_per_launch") if (B == 64) else None
         except Exception:
-            traffic = None
-    roofline = {"kernel": "frame_kernel<MODE_GL_ITER> (one Griffin-Lim iteration over the batch)", "bound": "hbm",
+            traffic, prof = None, {}
+    stream_kernel = os.environ.get("TTSA_GL_KERNEL", "") != "tile"
+    roofline = {"kernel": ("gl_stream_kernel" if stream_kernel else "frame_kernel<MODE_GL_ITER>") +
+                          " (one Griffin-Lim iteration over the batch)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                "traffic_source": (None if traffic is None else
+                                   "profiles/gl_iter_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                   "`ncu --set full` capture of this kernel at this batch (%s); committed constant, NOT "
+                                   "measured in this run" % prof.get("report", "?")),
                 "frac_of_nominal_8tbs": achieved / 8000.0,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": iter_ms,
                 "share_of_step": ITERS * iter_ms / ms_per_step,
                 "init_synthesis_ms": t_init}
+    # the roof that binds: the kernel executes a fixed number of FP32-pipe cycles per launch (ncu: sm__pipe_fma_cycles_active
+    # per SM, committed with the profile); 100 % pipe utilisation would finish them in cycles / clock
+    roofline_fp32 = None
+    if B == 64 and stream_kernel and prof.get("fma_pipe_cycles_per_sm"):
+        clk = 1e6 * float(clocks.get("sm_mhz") or prof.get("sm_mhz_nominal", 1965.0))
+        busy = float(prof["fma_pipe_cycles_per_sm"])
+        roofline_fp32 = {"bound": "fp32 pipe (FFMA2/FADD2/FMUL2 hold it two cycles, IMAD shares it)",
+                         "fma_pipe_cycles_per_sm_per_launch": busy, "sm_clock_hz": clk,
+                         "min_ms_at_full_pipe": 1e3 * busy / clk, "launch_ms": iter_ms,
+                         "frac": (busy / clk) / (iter_ms * 1e-3),
+                         "source": "profiles/gl_iter_traffic.json (ncu sm__pipe_fma_cycles_active.avg of the same capture); "
+                                   "the pipe-cycle count is a property of the instruction stream, the fraction uses this "
+                                   "run's live launch time"}
 
     line = {"metric": "griffin_lim_audio_sec_per_sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -410,7 +438,60 @@ def main():
             "config": config_dict(args, B), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "wall_ms_per_step": 1e3 * wall / args.steps},
-            "gpu_launches": launches, "cuda_graph": graph is not None, "roofline": roofline}
+            "gpu_launches": launches, "cuda_graph": graph is not None, "roofline": roofline,
+            "roofline_fp32": roofline_fp32}
+    if not (B == 64 and ITERS == 60):
+        line["configs4"] = {"total_utterances": world * B, "utterances_per_gpu": B, "griffin_lim_iters": ITERS, "gpus": world}
+
+    # ---- the literal drop-in call: one numpy [80, T] mel in, one numpy waveform out, per utterance (rank 0) ----
+    if rank == 0 and not args.no_extras:
+        mel_np = [np.ascontiguousarray(m.T) for m in mel.reshape(B, T_FRAMES, MELS)[:min(B, 64)].cpu().numpy()]
+        np.random.seed(0)
+        for m in mel_np[:3]:
+            ap.inv_mel_spectrogram(m)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_out = 0
+        for m in mel_np:
+            n_out += len(ap.inv_mel_spectrogram(m))
+        dt = time.perf_counter() - t0
+        line["e2e_dropin"] = {"value": n_out / SR / dt, "unit": "audio-s/s", "ms_per_utterance": 1e3 * dt / len(mel_np),
+                              "utterances": len(mel_np),
+                              "api": "AudioProcessor.inv_mel_spectrogram(np.ndarray [80, T]) -> np.ndarray, one call per "
+                                     "utterance, host arrays in and out, np.random phases drawn on the host as the "
+                                     "reference does (utils/audio.py:164-172, 183)"}
+        # BASELINE configs[0]: one 6 s linear spectrogram, inv_spectrogram, device resident
+        lay1 = ap.layout(n_frames=[T_FRAMES])
+        S1 = torch.rand((T_FRAMES, F), device=dev)
+        out1 = ap.inv_spectrogram_batch(S1, lay1)
+        torch.cuda.synchronize()
+        a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a1.record()
+        for _ in range(10):
+            out1 = ap.inv_spectrogram_batch(S1, lay1, out=out1)
+        b1.record()
+        torch.cuda.synchronize()
+        line["latency_single_ms"] = a1.elapsed_time(b1) / 10
+
+    # ---- optional final gather of the waveforms (north_star: "an optional final NCCL gather") ----
+    if args.gather and world > 1:
+        from your_voice_tts_b200.sharding import gather_packed
+        lens = torch.full((B,), L_OUT, dtype=torch.int64, device=dev)
+        gather_packed(wav_out, lens)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            blocks, totals, per_rank = gather_packed(wav_out, lens)
+        g1.record()
+        barrier()
+        t_g = torch.tensor([g0.elapsed_time(g1) / 5], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
+        nbytes = int(blocks.numel()) * 4
+        line["gather"] = {"ms": float(t_g.item()), "bytes_received_per_rank": nbytes,
+                          "GBps_per_rank": nbytes / (float(t_g.item()) * 1e-3) / 1e9, "backend": "nccl",
+                          "what": "sharding.gather_packed: every rank receives every rank's packed waveforms "
+                                  "(2 small all_gathers for sizes + 1 all_gather_into_tensor)"}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

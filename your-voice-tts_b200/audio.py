@@ -123,8 +123,23 @@ class HostPipeline(object):
         self.count = 0
         self.use_graph = bool(graph)
         self.graphs = [None, None]
+        self.graph_seeds = [None, None]
+        # the buffers were allocated (and zero-filled) on the caller's stream but are only ever used on the three side
+        # streams: order every side stream after the allocation, and tell the caching allocator about the other users
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        for s_ in (self.comp, self.copy, self.h2d):
+            s_.wait_event(ready)
+            for t_ in self.mel_dev + self.wav_dev + [self.lin_dev, self.ws]:
+                t_.record_stream(s_)
 
-    def _compute(self, b, seed):
+    def __del__(self):
+        try:
+            self.drain()                                   # no side-stream work may outlive the buffers
+        except Exception:
+            pass
+
+    def _compute(self, b, seed, init_angles=None):
         """mel -> |S|^power -> Griffin-Lim -> de-emphasis of buffer set b on the current stream."""
         ap, lay = self.ap, self.layout
         plan = lay.plan
@@ -132,21 +147,30 @@ class HostPipeline(object):
         L.check(plan.lib.ttsa_mel_to_linear(plan.handle, lay.handle, ap._ptr(self.mel_dev[b]), L.MEL_IN_NORM_DB,
                                             ap._ptr(self.lin_dev), L.MEL_OUT_POWER, st))
         L.check(plan.lib.ttsa_griffin_lim(plan.handle, lay.handle, ap._ptr(self.lin_dev), L.SPEC_MAGNITUDE,
-                                          int(ap.griffin_lim_iters), None, ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                          int(ap.griffin_lim_iters), None if init_angles is None else ap._ptr(init_angles),
+                                          ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
                                           L.GL_DEEMPHASIS if ap.preemphasis != 0 else 0, ap._ptr(self.wav_dev[b]), None,
                                           ap._ptr(self.ws), self.ws.numel(), st))
 
-    def submit(self, mel_host, wav_host, seed=0):
+    def submit(self, mel_host, wav_host, seed=0, init_angles=None, strict_seed=False):
+        """init_angles: optional device tensor [sum_T, num_freq] of initial phases (radians) instead of the counter RNG
+        (read while the batch computes: keep it alive and unchanged until the returned event).  With graph=True the
+        seed / init_angles of a buffer set are those of its first submit(); strict_seed=True raises when a later
+        submit() to that set passes a different seed instead of silently replaying the captured one."""
         torch = _torch()
         b = self.count & 1
         if self.use_graph and self.graphs[b] is None:
             with torch.cuda.stream(self.comp):
-                self._compute(b, seed)                          # warm-up outside capture
+                self._compute(b, seed, init_angles)             # warm-up outside capture
             self.comp.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.comp):
-                self._compute(b, seed)
+                self._compute(b, seed, init_angles)
             self.graphs[b] = g
+            self.graph_seeds[b] = int(seed)
+        elif self.use_graph and strict_seed and int(seed) != self.graph_seeds[b]:
+            raise ValueError("HostPipeline(graph=True): buffer set %d replays the graph captured with seed %d, not %d"
+                             % (b, self.graph_seeds[b], int(seed)))
         with torch.cuda.stream(self.h2d):
             if self.count >= 2:
                 self.h2d.wait_event(self.comp_done[b])         # batch i-2 has consumed this mel buffer
@@ -159,7 +183,7 @@ class HostPipeline(object):
             if self.use_graph:
                 self.graphs[b].replay()
             else:
-                self._compute(b, seed)
+                self._compute(b, seed, init_angles)
             self.comp_done[b].record(self.comp)
         with torch.cuda.stream(self.copy):
             self.copy.wait_event(self.comp_done[b])

@@ -30,6 +30,14 @@
 #include "common.cuh"
 #include "fft32p.cuh"
 
+// Phase-skipping timing probes exist only in profiling builds (build.py with TTSA_NVCC_EXTRA=-DTTSA_PROFILE_BUILD): the
+// shipped library cannot be told to skip work.
+#ifdef TTSA_PROFILE_BUILD
+#define TTSA_SKIP(a, bit) (((a).debug & (bit)) != 0)
+#else
+#define TTSA_SKIP(a, bit) false
+#endif
+
 namespace ttsa {
 
 enum { MODE_GL_ITER = 0, MODE_SYNTH = 1, MODE_ANALYSIS = 2 };
@@ -55,7 +63,8 @@ struct FrameArgs {
   float beta;             //   beta = momentum / (1 + momentum)   (fast Griffin-Lim, opt-in; not in the reference)
   int* wps_flags;         // warp-stream GL_ITER (gl_stream.cuh): per-warp "head zone stored" flag, compared with wps_epoch
   int wps_epoch;          //   (iteration number; ttsa_griffin_lim zeroes the flags once per call)
-  int debug;              // profiling only (TTSA_DEBUG): 1 = skip the frame phase, 2 = skip overlap-add + staging work
+  int debug;              // profiling builds only (-DTTSA_PROFILE_BUILD + env TTSA_DEBUG): 1 = skip the frame phase,
+                          // 2 = skip overlap-add + staging work; the shipped library compiles these branches out
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -351,7 +360,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         }
       }
       const int t = t0 + warp;
-      if (t < T && t >= first_needed && !(a.debug & 1)) {
+      if (t < T && t >= first_needed && !TTSA_SKIP(a, 1)) {
         const long long row = frow0 + t;
         const bool own = t >= ja * kNF;            // warm-up frames are copies of another segment's frames
         // 32 complex values per thread as packed pairs: R[m] = (re[2m], re[2m+1]), I[m] = (im[2m], im[2m+1])
@@ -687,7 +696,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
       // warp waits for the others and while the tile is overlap-added (the planes are rewritten after that)
       const bool have_next = jt + 1 < jb;
       if constexpr (MODE != MODE_SYNTH) {
-        if (have_next && !(a.debug & 2)) stage_load(jt + 1);
+        if (have_next && !TTSA_SKIP(a, 2)) stage_load(jt + 1);
       }
       __syncthreads();                             // slots complete; planes consumed
 
@@ -782,7 +791,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
             }
           }
         };
-        if (!(a.debug & 2)) {
+        if (!TTSA_SKIP(a, 2)) {
           if (tid < kThreads / 2) {
             ola(IntC<0>{}, IntC<0>{});
           } else {
@@ -792,7 +801,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         // residues beyond the thread count (hop 275 = 256 + 19): one small item per (residue, j mod kNF) spread over
         // all warps; a second full round for the few threads that own one would sit on the tile's critical path
         // (measured: 0.160 vs 0.155 ms per iteration)
-        if (ly.hop > kThreads && !(a.debug & 2)) {
+        if (ly.hop > kThreads && !TTSA_SKIP(a, 2)) {
           const int nl = ly.hop - kThreads;
           for (int it = tid; it < nl * kNF; it += kThreads) {
             const int jl = it / nl, rr = kThreads + it - jl * nl;
@@ -819,7 +828,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
       }
 
       if constexpr (MODE != MODE_SYNTH) {
-        if (have_next && !(a.debug & 2)) stage_store(jt + 1);
+        if (have_next && !TTSA_SKIP(a, 2)) stage_store(jt + 1);
       }
       __syncthreads();                             // planes of the next tile ready; slots and carry settled
     }  // tiles of the segment

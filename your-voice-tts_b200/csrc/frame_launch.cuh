@@ -62,14 +62,17 @@ inline const char* set_smem(K kernel, size_t /*smem_bytes*/) {
 // get class-20 kernels with the geometry as template constants; everything else runs the run-time-geometry kernels.
 #define TTSA_FIXED_GEOS(X) X(275, 1102) X(200, 800) X(300, 1200)
 
+// The opt-in momentum variant (fast Griffin-Lim, not in the reference) is instantiated for run-time geometry only.
 template <int MODE, int SRC, bool SC, bool MOM = false>
 inline const char* configure_variants(size_t smem_bytes) {
   const char* e;
   if ((e = set_smem(frame_kernel<MODE, SRC, 20, SC, 0, 0, MOM>, smem_bytes))) return e;
   if ((e = set_smem(frame_kernel<MODE, SRC, 32, SC, 0, 0, MOM>, smem_bytes))) return e;
+  if constexpr (!MOM) {
 #define TTSA_X(H, W) if ((e = set_smem(frame_kernel<MODE, SRC, 20, SC, H, W, MOM>, smem_bytes))) return e;
-  TTSA_FIXED_GEOS(TTSA_X)
+    TTSA_FIXED_GEOS(TTSA_X)
 #undef TTSA_X
+  }
   return nullptr;
 }
 
@@ -77,10 +80,12 @@ template <int MODE, int SRC, bool SC, bool MOM = false>
 inline const char* launch_variant(int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo& g, const Tables& tb,
                                   const BatchDev& bd, const FrameArgs& a) {
   if (nz != 20) TTSA_LAUNCH((frame_kernel<MODE, SRC, 32, SC, 0, 0, MOM>));
-  if (fixed) {
+  if constexpr (!MOM) {
+    if (fixed) {
 #define TTSA_X(H, W) if (g.ly.hop == H && g.ly.win == W) TTSA_LAUNCH((frame_kernel<MODE, SRC, 20, SC, H, W, MOM>));
-    TTSA_FIXED_GEOS(TTSA_X)
+      TTSA_FIXED_GEOS(TTSA_X)
 #undef TTSA_X
+    }
   }
   TTSA_LAUNCH((frame_kernel<MODE, SRC, 20, SC, 0, 0, MOM>));
 }

@@ -348,12 +348,13 @@ __global__ void __launch_bounds__(kM2lThreads, 1) mel_to_linear_tc_kernel(const 
     const long long row0 = (long long)mt * kTcRows;
     __syncthreads();                                // previous M tile fully drained (staging, A, B reusable)
     load_b(0);
-    // ---- A: fp32 mel -> amplitude -> three bf16 terms; thread (row, half) converts 5 K blocks of 8
-    if (tid < 256) {
-      const int r = tid >> 1, half = tid & 1;
+    // ---- A: fp32 mel -> amplitude -> three bf16 terms; thread (row, quarter) converts 3 / 3 / 2 / 2 K blocks of 8
+    {
+      const int r = tid >> 2, quarter = tid & 3;
       const long long row = row0 + r;
+      const int kb0 = quarter < 2 ? 3 * quarter : 6 + 2 * (quarter - 2), kb1 = kb0 + (quarter < 2 ? 3 : 2);
 #pragma unroll 1
-      for (int kb = half * 5; kb < half * 5 + 5; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         __align__(16) __nv_bfloat16 h8[8], m8[8], l8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -399,6 +400,7 @@ __global__ void __launch_bounds__(kM2lThreads, 1) mel_to_linear_tc_kernel(const 
       if (nt >= 1) epilogue(nt - 1, row0);
       if (nt + 1 < kM2lTiles) load_b(nt + 1);
     }
+    __syncthreads();                                // the row stores of tile kM2lTiles-2 have read the staging buffer
     epilogue(kM2lTiles - 1, row0);
   }
   __syncthreads();

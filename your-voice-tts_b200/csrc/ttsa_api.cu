@@ -64,7 +64,7 @@ struct ttsa_plan {
   std::vector<double> h_inv_mel;   // [F][num_mels]
   int nz = 32;                     // compile-time zero-pruning class of the frame kernels (20 or 32)
   int ctas_per_sm = 1;
-  int debug = 0;                   // TTSA_DEBUG (profiling: skip phases of the iteration kernel), read once per plan
+  int debug = 0;                   // profiling builds only (TTSA_PROFILE_BUILD + env TTSA_DEBUG): skip phases of the tile kernel
   int mel_gemm = 0;                // TTSA_MEL_GEMM: 0 default (tensor cores), 1 "simt", 2 "tc_simple"
   bool generic = false;            // n_fft != 2048: the any-size kernels of generic_kernels.cuh
   GenGeo gg;
@@ -350,7 +350,13 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   }
   DeviceGuard guard(device);
   cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  {
+    const cudaError_t pe = cudaGetDeviceProperties(&prop, device);
+    if (pe != cudaSuccess) {
+      delete p;
+      return fail(TTSA_ERR_CUDA, "cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(pe));
+    }
+  }
   if (prop.major != 10) {
     delete p;
     return fail(TTSA_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
@@ -551,7 +557,9 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     }
   }
   { const char* gen = std::getenv("TTSA_GENERIC_GEO"); p->fixed_geo = !(gen != nullptr && std::atoi(gen) != 0); }
+#ifdef TTSA_PROFILE_BUILD
   { const char* dbg = std::getenv("TTSA_DEBUG"); p->debug = dbg ? std::atoi(dbg) : 0; }
+#endif
   { const char* mg = std::getenv("TTSA_MEL_GEMM");
     p->mel_gemm = mg == nullptr ? 0 : (std::strcmp(mg, "simt") == 0 ? 1 : (std::strcmp(mg, "tc_simple") == 0 ? 2 : 0)); }
   cudaError_t e = cudaFuncSetAttribute(mel_to_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1005,6 +1013,7 @@ extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* ba
   if (workspace_bytes < ttsa_griffin_lim_workspace_bytes(plan, batch)) return fail(TTSA_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, ttsa_griffin_lim_workspace_bytes(plan, batch));
   const bool deemph = (flags & TTSA_GL_DEEMPHASIS) != 0;
   if (deemph && plan->cfg.preemphasis == 0.0) return fail(TTSA_ERR_BAD_CONFIG, " !! Preemphasis is applied with factor 0.0. ");
+  if (deemph && plan->cfg.preemphasis < 0.0) return fail(TTSA_ERR_UNSUPPORTED, "de-emphasis with a negative coefficient (%g) is not supported", plan->cfg.preemphasis);
   DeviceGuard guard(plan->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t wav_bytes = ((size_t)batch->total_samples * 4 + 255) / 256 * 256 + 256;

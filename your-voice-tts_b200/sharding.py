@@ -3,7 +3,7 @@ frame-balanced shards (one process per GPU) and no collective touches the data p
 final gather of the synthesised waveforms (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
 import numpy as np
 
-__all__ = ["partition_utterances", "shard_for_rank", "gather_waveforms"]
+__all__ = ["partition_utterances", "shard_for_rank", "gather_waveforms", "gather_packed"]
 
 
 def partition_utterances(n_frames, world_size):
@@ -33,38 +33,58 @@ def shard_for_rank(n_frames, world_size, rank):
     return partition_utterances(n_frames, world_size)[rank]
 
 
-def gather_waveforms(local_wavs, group=None):
-    """All-gather variable-length waveforms: every rank receives the rank-ordered list of all waveforms.
+def gather_packed(packed, lengths, group=None):
+    """All-gather packed waveform buffers: the optional final exchange of the sharded path (the server concatenates the
+    sentences of a request in order, server/synthesizer.py:157-161).
 
-    local_wavs: list of 1-D float32 tensors (this rank's shard, device = the backend's device).
-    One all_gather of the lengths and one all_gather of a padded [n_local_max, len_max] block.
+    packed:  1-D float32 tensor, this rank's waveforms back to back (the layout the kernels write; padding between
+             utterances is allowed and travels as it is).
+    lengths: 1-D int64 tensor / list with this rank's per-utterance sample counts.
+    Two small all_gathers for the sizes and ONE all_gather_into_tensor for the samples (every rank contributes a block
+    padded to the largest shard).  Returns (blocks [world, max_total] float32, totals [world] int64, per-rank length
+    tensors); rank r's samples are blocks[r, :totals[r]].
     """
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    dev = packed.device
+    lengths = torch.as_tensor(lengths, dtype=torch.int64, device=dev).reshape(-1)
+    meta = torch.tensor([int(packed.numel()), int(lengths.numel())], dtype=torch.int64, device=dev)
+    metas = torch.zeros((world, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas.reshape(-1), meta, group=group)
+    metas_h = metas.cpu()
+    max_total, max_n = int(metas_h[:, 0].max()), int(metas_h[:, 1].max())
+    len_block = torch.zeros((max(max_n, 1),), dtype=torch.int64, device=dev)
+    len_block[:lengths.numel()] = lengths
+    len_blocks = torch.zeros((world, max(max_n, 1)), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(len_blocks.reshape(-1), len_block, group=group)
+    if int(packed.numel()) == max_total:
+        mine = packed.reshape(-1)
+    else:
+        mine = torch.zeros((max(max_total, 1),), dtype=torch.float32, device=dev)
+        mine[:packed.numel()] = packed.reshape(-1)
+    blocks = torch.empty((world, max(max_total, 1)), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(blocks.reshape(-1), mine, group=group)
+    per_rank = [len_blocks[r, :int(metas_h[r, 1])] for r in range(world)]
+    return blocks, metas_h[:, 0].clone(), per_rank
+
+
+def gather_waveforms(local_wavs, group=None):
+    """All-gather variable-length waveforms: every rank receives the rank-ordered list of all waveforms (views into one
+    gathered block, no per-utterance copies).  local_wavs: list of 1-D float32 tensors (this rank's shard)."""
+    import torch
+    import torch.distributed as dist
     if len(local_wavs) > 0:
         dev = local_wavs[0].device
     else:
         dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    lens = torch.tensor([int(w.numel()) for w in local_wavs], dtype=torch.int64, device=dev)
-    meta = torch.tensor([len(local_wavs), int(lens.max()) if len(local_wavs) else 0], dtype=torch.int64, device=dev)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    n_max = max(int(m[0]) for m in metas)
-    l_max = max(int(m[1]) for m in metas)
-    if n_max == 0:
-        return []
-    len_block = torch.zeros((n_max,), dtype=torch.int64, device=dev)
-    len_block[:len(local_wavs)] = lens
-    block = torch.zeros((n_max, max(l_max, 1)), dtype=torch.float32, device=dev)
-    for i, w in enumerate(local_wavs):
-        block[i, :w.numel()] = w
-    len_blocks = [torch.zeros_like(len_block) for _ in range(world)]
-    blocks = [torch.zeros_like(block) for _ in range(world)]
-    dist.all_gather(len_blocks, len_block, group=group)
-    dist.all_gather(blocks, block, group=group)
+    lens = [int(w.numel()) for w in local_wavs]
+    packed = torch.cat([w.reshape(-1) for w in local_wavs]) if local_wavs else torch.zeros((0,), dtype=torch.float32, device=dev)
+    blocks, totals, per_rank = gather_packed(packed, lens, group=group)
     out = []
-    for r in range(world):
-        for i in range(int(metas[r][0])):
-            out.append(blocks[r][i, :int(len_blocks[r][i])].clone())
+    for r in range(blocks.shape[0]):
+        off = 0
+        for n in per_rank[r].tolist():
+            out.append(blocks[r, off:off + n])
+            off += n
     return out
