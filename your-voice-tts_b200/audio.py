@@ -77,6 +77,9 @@ class BatchLayout(object):
                                        wo.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                                        wl.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
         self.frame_off, self.wav_off, self.wav_len = fo, wo, wl
+        # samples a packed waveform buffer must hold: up to the last utterance's last sample (total_samples also counts
+        # the padding that keeps every utterance 16-byte aligned)
+        self.need_samples = int(wo[self.n_utts - 1] + wl[self.n_utts - 1]) if self.n_utts > 0 else 0
         self.n_frames = (np.asarray(src, dtype=np.int64).reshape(-1) if n_frames is not None
                          else 1 + wl.astype(np.int64) // plan.cfg.hop_length)
 
@@ -359,6 +362,12 @@ class AudioProcessor(object):
         return t.cpu().numpy()
 
     # ------------------------------------------------------------------------------------------ batched API
+    @staticmethod
+    def _need(t, n, what):
+        """The C ABI takes bare pointers: the sizes the kernels will touch are checked here, on the host side."""
+        if t is not None and int(t.numel()) < int(n):
+            raise ValueError("%s holds %d elements, the batch layout needs %d" % (what, int(t.numel()), int(n)))
+
     def features_batch(self, wav_packed, layout, want_linear=True, want_mel=True, preemphasis=None, lin_out=None,
                        mel_out=None):
         """spectrogram() and melspectrogram() of every utterance in one pass (utils/audio.py:138-152).
@@ -373,6 +382,9 @@ class AudioProcessor(object):
         if mel is None and want_mel:
             mel = torch.empty((layout.total_frames, self.num_mels), dtype=torch.float32, device=wav_packed.device)
         pre = (self.preemphasis != 0) if preemphasis is None else bool(preemphasis)
+        self._need(wav_packed, layout.need_samples, "wav_packed")
+        self._need(lin, layout.total_frames * self.num_freq, "linear output")
+        self._need(mel, layout.total_frames * self.num_mels, "mel output")
         L.check(plan.lib.ttsa_stft_features(plan.handle, layout.handle, self._ptr(wav_packed), self._ptr(lin),
                                             self._ptr(mel), L.FEAT_PREEMPHASIS if pre else 0, self._stream()))
         return lin, mel
@@ -381,6 +393,7 @@ class AudioProcessor(object):
         torch = _torch()
         plan = layout.plan
         out = torch.empty((layout.total_frames, self.num_freq, 2), dtype=torch.float32, device=wav_packed.device)
+        self._need(wav_packed, layout.need_samples, "wav_packed")
         L.check(plan.lib.ttsa_stft(plan.handle, layout.handle, self._ptr(wav_packed), self._ptr(out), self._stream()))
         return out
 
@@ -388,6 +401,7 @@ class AudioProcessor(object):
         torch = _torch()
         plan = layout.plan
         out = torch.zeros((max(1, layout.total_samples),), dtype=torch.float32, device=stft_packed.device)
+        self._need(stft_packed, layout.total_frames * self.num_freq * 2, "stft_packed")
         L.check(plan.lib.ttsa_istft(plan.handle, layout.handle, self._ptr(stft_packed), self._ptr(out), self._stream()))
         return out
 
@@ -408,6 +422,10 @@ class AudioProcessor(object):
             workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         sc = torch.empty((max(1, iters), layout.n_utts, 2), dtype=torch.float32, device=dev) if return_sc else None
         momentum = float(getattr(self, "griffin_lim_momentum", 0.0) if momentum is None else momentum)
+        self._need(spec_packed, layout.total_frames * self.num_freq, "spec_packed")
+        self._need(init_angles, layout.total_frames * self.num_freq, "init_angles")
+        self._need(out, layout.need_samples, "waveform output")
+        self._need(workspace, ws_bytes, "workspace")
         L.check(plan.lib.ttsa_griffin_lim_fast(plan.handle, layout.handle, self._ptr(spec_packed), int(spec_kind), iters,
                                                self._ptr(init_angles), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
                                                L.GL_DEEMPHASIS if deemphasis else 0, momentum, self._ptr(out),
@@ -421,6 +439,7 @@ class AudioProcessor(object):
         torch = _torch()
         plan = layout.plan
         out = torch.empty((layout.total_frames, self.num_freq), dtype=torch.float32, device=mel_packed.device)
+        self._need(mel_packed, layout.total_frames * self.num_mels, "mel_packed")
         L.check(plan.lib.ttsa_mel_to_linear(plan.handle, layout.handle, self._ptr(mel_packed), in_kind,
                                             self._ptr(out), out_kind, self._stream()))
         return out
@@ -429,6 +448,7 @@ class AudioProcessor(object):
         torch = _torch()
         plan = layout.plan
         out = torch.empty((layout.total_frames, self.num_mels), dtype=torch.float32, device=lin_packed.device)
+        self._need(lin_packed, layout.total_frames * self.num_freq, "lin_packed")
         L.check(plan.lib.ttsa_linear_to_mel(plan.handle, layout.handle, self._ptr(lin_packed), in_kind,
                                             self._ptr(out), out_kind, self._stream()))
         return out
