@@ -187,6 +187,40 @@ def test_large_batch_segments_deterministic_and_match_oracle():
     assert snr_db(lay.split_wav(y1)[37].cpu().numpy(), y_single[:275 * (T - 1)].cpu().numpy()) >= 120.0
 
 
+def test_small_batch_fine_segments(monkeypatch):
+    """Batches too small to fill the GPU (the server synthesises one sentence at a time, server/synthesizer.py:147-157)
+    run the iteration kernel with one CTA per fine segment (8 frames, then 4 owned + 4 recomputed frames each).  Checked
+    against the oracle and against the ordinary tile partition (TTSA_GL_FINE=0), for frame counts around every boundary."""
+    from your_voice_tts_b200 import audio as A
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=5)
+    orc = OracleAudioProcessor(**audio)
+    rng = np.random.default_rng(17)
+    cases = [[1], [2], [7], [8], [9], [12], [13], [61], [482], [100, 3, 57]]
+    data = [([rng.random((T, 1025)).astype(np.float32) for T in Ts],
+             [(2 * np.pi * rng.random((T, 1025))).astype(np.float32) for T in Ts]) for Ts in cases]
+    outs = {}
+    for fine in ("1", "0"):
+        monkeypatch.setenv("TTSA_GL_FINE", fine)
+        A._PLAN_CACHE.clear()
+        ap = _ap(audio)
+        for Ts, (specs, angs) in zip(cases, data):
+            lay = ap.layout(n_frames=Ts)
+            y = ap.inv_spectrogram_batch(torch.from_numpy(np.concatenate(specs)).cuda(), lay,
+                                         init_angles=torch.from_numpy(np.concatenate(angs)).cuda())
+            outs[(fine, tuple(Ts))] = [w.cpu().numpy().copy() for w in lay.split_wav(y)]
+    monkeypatch.delenv("TTSA_GL_FINE")
+    A._PLAN_CACHE.clear()
+    for Ts, (specs, angs) in zip(cases, data):
+        for u, T in enumerate(Ts):
+            if T < 2:
+                continue
+            yf, yt = outs[("1", tuple(Ts))][u], outs[("0", tuple(Ts))][u]
+            yo = orc.inv_spectrogram(specs[u].T, init_angles=angs[u].T)
+            assert yf.shape == yo.shape
+            assert snr_db(yo, yf) >= GL_SNR_DB, (Ts, u, snr_db(yo, yf))
+            assert snr_db(yt, yf) >= 110.0, (Ts, u, snr_db(yt, yf))
+
+
 def test_generic_geometry_kernel_class():
     """win 1764 / hop 275 (80 ms window): more than 5 taps per hop residue and 28 non-zero packed rows -> the generic
     (NZ = 32) kernel class; and win 2048 == n_fft."""

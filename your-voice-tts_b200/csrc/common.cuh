@@ -104,8 +104,10 @@ struct BatchDev {
   const long long* frame_off;// [B+1]
   const long long* wav_off;  // [B+1] (multiples of 4)
   const int* tile_off;       // [B+1] prefix sum of ceil(T/kNF)
+  const int* fine_off;       // [B+1] prefix sum of the fine segments per utterance (frame_kernel<..., FINE>)
   int B;
   int total_tiles;
+  int total_fine;
 };
 
 #ifndef TTSA_WPS_WARPS

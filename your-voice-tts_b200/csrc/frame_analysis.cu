@@ -23,8 +23,8 @@ const char* configure_frame_kernels(size_t smem_bytes, int* ctas_per_sm) {
 }
 
 const char* launch_frame_kernel(int mode, int src, int nz, bool sc, bool fixed, bool mom, int grid, size_t smem_bytes, cudaStream_t st,
-                                const Geo& g, const Tables& tb, const BatchDev& bd, const FrameArgs& a) {
-  if (mode == MODE_GL_ITER) return launch_gl(src, nz, sc, fixed, mom, grid, smem_bytes, st, g, tb, bd, a);
+                                const Geo& g, const Tables& tb, const BatchDev& bd, const FrameArgs& a, bool fine) {
+  if (mode == MODE_GL_ITER) return launch_gl(src, nz, sc, fixed, mom, grid, smem_bytes, st, g, tb, bd, a, fine);
   if (mode == MODE_SYNTH) return launch_synth(src, nz, fixed, grid, smem_bytes, st, g, tb, bd, a);
   return launch_analysis(src, nz, fixed, grid, smem_bytes, st, g, tb, bd, a);
 }

@@ -186,7 +186,11 @@ __device__ __forceinline__ float2 shfl2(float a, float b, int srclane) {
 }
 
 // HOP, WIN > 0: geometry fixed at compile time (the shipped configurations); 0: read from Geo at run time.
-template <int MODE, int SRC, int NZ, bool SC, int HOP = 0, int WIN = 0, bool MOM = false>
+// FINE (Griffin-Lim iteration on batches too small to fill the GPU, e.g. the server's one sentence at a time,
+// server/synthesizer.py:147-157): one CTA per "fine segment" -- the utterance's first 8 frames, then 8 - nwarm owned frames
+// each -- and ONE tile per CTA whose first nwarm frames are the recomputed neighbours.  A 6 s utterance then occupies 120
+// CTAs for one tile phase per iteration instead of 61 CTAs for two (warm-up tile + own tile).
+template <int MODE, int SRC, int NZ, bool SC, int HOP = 0, int WIN = 0, bool MOM = false, bool FINE = false>
 __global__ void __launch_bounds__(kThreads, 2)
 frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -245,18 +249,19 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
   // the batch layout and the (constant) spectrogram happens BEFORE the dependency wait below: the utterance search is a
   // chain of dependent global loads, and the first tile's |S| rows can already travel towards L2.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const long long tile_lo = (long long)blockIdx.x * bd.total_tiles / gridDim.x;
-  const long long tile_hi = (long long)(blockIdx.x + 1) * bd.total_tiles / gridDim.x;
+  const long long tile_lo = FINE ? (long long)blockIdx.x : (long long)blockIdx.x * bd.total_tiles / gridDim.x;
+  const long long tile_hi = FINE ? (long long)blockIdx.x + 1 : (long long)(blockIdx.x + 1) * bd.total_tiles / gridDim.x;
+  const int* const seg_off = FINE ? bd.fine_off : bd.tile_off;      // prefix sums of the work list this launch walks
   int u = 0;
   {
-    int lo = 0, hi = bd.B;   // largest u with tile_off[u] <= tile_lo
+    int lo = 0, hi = bd.B;   // largest u with seg_off[u] <= tile_lo
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if (bd.tile_off[mid] <= tile_lo) lo = mid; else hi = mid;
+      if (seg_off[mid] <= tile_lo) lo = mid; else hi = mid;
     }
     u = lo;
   }
-  if constexpr (MODE == MODE_GL_ITER) {
+  if constexpr (MODE == MODE_GL_ITER && !FINE) {
     if (tile_lo < tile_hi) {
       const int t_first = (int)(tile_lo - bd.tile_off[u]) * kNF;
       const int n_rows = min(kNF, bd.T[u] - t_first);
@@ -271,12 +276,18 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
 
   long long tile = tile_lo;
   while (tile < tile_hi) {
-    while (u + 1 < bd.B && tile >= bd.tile_off[u + 1]) ++u;
+    while (u + 1 < bd.B && tile >= seg_off[u + 1]) ++u;
     const int T = bd.T[u];
-    const int toff = bd.tile_off[u];
-    const int ja = (int)(tile - toff);
-    const long long seg_end = tile_hi < (long long)bd.tile_off[u + 1] ? tile_hi : (long long)bd.tile_off[u + 1];
-    const int jb = (int)(seg_end - toff);
+    const int toff = seg_off[u];
+    const long long seg_end = tile_hi < (long long)seg_off[u + 1] ? tile_hi : (long long)seg_off[u + 1];
+    // fine segment s of the utterance: owned frames [sfa, sfb), tile origin t0f (its first sfa - t0f frames are warm-up)
+    const int fs = (int)(tile - toff);
+    const int fown = kNF - ly.nwarm;
+    const int sfa = FINE ? (fs == 0 ? 0 : kNF + (fs - 1) * fown) : 0;
+    const int sfb = FINE ? min(T, fs == 0 ? kNF : sfa + fown) : T;
+    const int t0f = FINE ? (fs == 0 ? 0 : sfa - ly.nwarm) : 0;
+    const int ja = FINE ? 0 : (int)(tile - toff);
+    const int jb = FINE ? 1 : (int)(seg_end - toff);
     tile = seg_end;
     const int L = bd.wav_len[u];                 // signal length (GL / SYNTH: hop*(T-1))
     if (MODE != MODE_ANALYSIS && L <= 0) continue;
@@ -286,8 +297,8 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     const float* __restrict__ srcp = MOM ? a.wav_prev + woff : nullptr;     // fast Griffin-Lim: previous estimate
 
     // frames of earlier tiles still overlap this segment's first owned sample: recompute them (no output)
-    const bool warm = (MODE != MODE_ANALYSIS) && ja > 0 && ly.nwarm > 0;
-    const int first_needed = warm ? ja * kNF - ly.nwarm : 0;
+    const bool warm = !FINE && (MODE != MODE_ANALYSIS) && ja > 0 && ly.nwarm > 0;
+    const int first_needed = FINE ? t0f : (warm ? ja * kNF - ly.nwarm : 0);
     const int jt_first = warm ? ja - 1 : ja;
     bool has_carry = false;
     float sc_num = 0.0f, sc_den = 0.0f;
@@ -296,7 +307,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     //      re/im frame loads are conflict-free
     float stg[kStage];
     auto stage_load = [&](int jt) {
-      const int i0 = jt * kNF * ly.hop - ly.off0;
+      const int i0 = (FINE ? t0f : jt * kNF) * ly.hop - ly.off0;
       if (i0 >= 1 && i0 + ly.span_len <= L) {                       // interior span: no reflection
         const float* __restrict__ sp = src + i0;
 #pragma unroll
@@ -330,7 +341,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
 #pragma unroll
       for (int e = 0; e < kStage; ++e)
         if (tid + e * kThreads < ly.span_len) pl[e * (kThreads / 2)] = stg[e];
-      const int i0 = jt * kNF * ly.hop - ly.off0;
+      const int i0 = (FINE ? t0f : jt * kNF) * ly.hop - ly.off0;
       for (int s = tid + kStage * kThreads; s < ly.span_len; s += kThreads) {     // spans longer than the register window
         const int j = reflect_index(i0 + s, L);
         float val = __ldg(src + j);
@@ -348,7 +359,7 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
     }
 
     for (int jt = jt_first; jt < jb; ++jt) {
-      const int t0 = jt * kNF;
+      const int t0 = FINE ? t0f : jt * kNF;
       const int i0 = t0 * ly.hop - ly.off0;        // sample index of span position 0
       const bool write_out = jt >= ja;
 
@@ -360,9 +371,9 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         }
       }
       const int t = t0 + warp;
-      if (t < T && t >= first_needed && !TTSA_SKIP(a, 1)) {
+      if (t < sfb && t >= first_needed && !TTSA_SKIP(a, 1)) {
         const long long row = frow0 + t;
-        const bool own = t >= ja * kNF;            // warm-up frames are copies of another segment's frames
+        const bool own = FINE ? t >= sfa : t >= ja * kNF;   // warm-up frames are copies of another segment's frames
         // 32 complex values per thread as packed pairs: R[m] = (re[2m], re[2m+1]), I[m] = (im[2m], im[2m+1])
         float2 R[16], I[16];
         int s_off = 0;
@@ -707,15 +718,21 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
         // lanes read consecutive addresses of alternating slot planes.  The carry (samples that later frames still
         // add to) is read and re-written by the same thread.
         const int fv_lo = first_needed > t0 ? first_needed - t0 : 0;
-        const int fv_hi = (T - t0) < kNF ? (T - t0) : kNF;
-        // the utterance's last tile also flushes what would be its carry (samples up to hop*(T-1) end there)
-        const int out_len = (t0 + kNF >= T) ? ly.span_len : kNF * ly.hop;
+        const int fv_hi = (sfb - t0) < kNF ? (sfb - t0) : kNF;
+        // the utterance's last tile also flushes what would be its carry (samples up to hop*(T-1) end there); a fine
+        // segment writes [own_lo, out_len): what lies before belongs to the previous segment, what follows to the next
+        const int out_len = FINE ? (sfb >= T ? ly.span_len : (sfb - t0) * ly.hop) : ((t0 + kNF >= T) ? ly.span_len : kNF * ly.hop);
+        const int own_lo = FINE ? (sfa - t0) * ly.hop : 0;
         float* __restrict__ dst = a.wav_out + woff;
-        const bool interior = write_out && fv_lo == 0 && fv_hi == kNF && i0 >= 0 && t0 + kNF < T &&
+        const bool interior = !FINE && write_out && fv_lo == 0 && fv_hi == kNF && i0 >= 0 && t0 + kNF < T &&
                               i0 + kNF * ly.hop <= L && t0 >= ND - 1;
+        // a full fine tile away from the utterance's ends: positions [nwarm*hop, 8*hop) are written, nothing is carried
+        const bool interior_fine = FINE && fs > 0 && fv_hi == kNF && sfb < T && i0 >= 0 && i0 + kNF * ly.hop <= L &&
+                                   t0 >= ND - 1;
         // finished sample `val` at span position sidx = j*hop + rr: scale and store, or keep as carry
         auto emit = [&](int j, int rr, int sidx, float val) {
           if (sidx >= ly.span_len) return;
+          if (FINE && (sidx < own_lo || sidx >= out_len)) return;
           if (sidx < out_len) {
             const int i = i0 + sidx;
             if (write_out && i >= 0 && i < L) {
@@ -774,6 +791,17 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               const int c = (j - kNF) * ly.hop + rr;
               if (c < ly.carry_len) carry[c] = acc[j];
             }
+          } else if (interior_fine) {
+#pragma unroll
+            for (int f = 0; f < kNF; ++f) {
+#pragma unroll
+              for (int d = 0; d < ND; ++d) acc[f + d] = fmaf(sl0[f * kBufFloats + off[d]], wreg[d], acc[f + d]);
+            }
+            const float inv = pw[rr];
+            float* __restrict__ po = dst + (i0 + rr);
+#pragma unroll
+            for (int j = 0; j < kNF; ++j)
+              if (j >= ly.nwarm) po[j * ly.hop] = acc[j] * inv;
           } else {
 #pragma unroll
             for (int f = 0; f < kNF; ++f) {
@@ -818,6 +846,8 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
             if (interior) {   // owned, inside the signal, every overlapping frame exists: no edge handling
               dst[i0 + sa] = va * pw[rr];
               if (jl < ND - 1 && sb < ly.span_len) carry[sb - kNF * ly.hop] = vb;
+            } else if (interior_fine) {
+              if (jl >= ly.nwarm) dst[i0 + sa] = va * pw[rr];
             } else {
               emit(jl, rr, sa, va);
               if (jl < ND - 1) emit(jl + kNF, rr, sb, vb);

@@ -11,13 +11,13 @@ extern std::atomic<unsigned long long> g_launches;
 // Griffin-Lim iteration kernel.  Returns nullptr or an error string.
 const char* configure_frame_kernels(size_t smem_bytes, int* ctas_per_sm);
 const char* launch_frame_kernel(int mode, int src, int nz, bool sc, bool fixed, bool mom, int grid, size_t smem_bytes, cudaStream_t st,
-                                const Geo& g, const Tables& tb, const BatchDev& bd, const FrameArgs& a);
+                                const Geo& g, const Tables& tb, const BatchDev& bd, const FrameArgs& a, bool fine = false);
 
 // per translation unit
 const char* configure_gl(size_t smem_bytes, int* ctas_per_sm);
 const char* configure_synth(size_t smem_bytes);
 const char* configure_analysis(size_t smem_bytes);
-const char* launch_gl(int src, int nz, bool sc, bool fixed, bool mom, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
+const char* launch_gl(int src, int nz, bool sc, bool fixed, bool mom, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&, bool fine = false);
 const char* launch_synth(int src, int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 const char* launch_analysis(int out, int nz, bool fixed, int grid, size_t smem, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&);
 
@@ -74,6 +74,27 @@ inline const char* configure_variants(size_t smem_bytes) {
 #undef TTSA_X
   }
   return nullptr;
+}
+
+// fine-segment form of the Griffin-Lim iteration (small batches; no spectral-convergence sums, no momentum)
+template <int SRC>
+inline const char* configure_fine(size_t smem_bytes) {
+  const char* e;
+  if ((e = set_smem(frame_kernel<MODE_GL_ITER, SRC, 20, false, 0, 0, false, true>, smem_bytes))) return e;
+#define TTSA_X(H, W) if ((e = set_smem(frame_kernel<MODE_GL_ITER, SRC, 20, false, H, W, false, true>, smem_bytes))) return e;
+  TTSA_FIXED_GEOS(TTSA_X)
+#undef TTSA_X
+  return nullptr;
+}
+template <int SRC>
+inline const char* launch_fine(bool fixed, int grid, size_t smem, cudaStream_t st, const Geo& g, const Tables& tb,
+                               const BatchDev& bd, const FrameArgs& a) {
+  if (fixed) {
+#define TTSA_X(H, W) if (g.ly.hop == H && g.ly.win == W) TTSA_LAUNCH((frame_kernel<MODE_GL_ITER, SRC, 20, false, H, W, false, true>));
+    TTSA_FIXED_GEOS(TTSA_X)
+#undef TTSA_X
+  }
+  TTSA_LAUNCH((frame_kernel<MODE_GL_ITER, SRC, 20, false, 0, 0, false, true>));
 }
 
 template <int MODE, int SRC, bool SC, bool MOM = false>

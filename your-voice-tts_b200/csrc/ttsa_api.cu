@@ -69,6 +69,7 @@ struct ttsa_plan {
   bool generic = false;            // n_fft != 2048: the any-size kernels of generic_kernels.cuh
   GenGeo gg;
   GenTables gt;
+  bool fine_ok = true;             // small batches may use the fine-segment form of the tile kernel (TTSA_GL_FINE=0: never)
   bool fixed_geo = true;           // use the kernels compiled for this (hop, win) when they exist (TTSA_GENERIC_GEO=1: never)
   int wps_grid = 0;                // CTAs of the warp-stream kernel (= SMs; TTSA_WPS_GRID overrides it for tests)
   bool gl_stream = false;          // Griffin-Lim iterations run the warp-stream kernel (gl_stream.cuh) when the batch has a
@@ -88,7 +89,7 @@ struct ttsa_batch {
   int device = -1;
   int B = 0;
   int hop = 0;
-  std::vector<int> T, wav_len, tile_off, chunk_off;
+  std::vector<int> T, wav_len, tile_off, chunk_off, fine_off;
   std::vector<long long> frame_off, wav_off;
   long long total_frames = 0, total_samples = 0;
   int max_chunks = 0;
@@ -557,6 +558,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     }
   }
   { const char* gen = std::getenv("TTSA_GENERIC_GEO"); p->fixed_geo = !(gen != nullptr && std::atoi(gen) != 0); }
+  { const char* fi = std::getenv("TTSA_GL_FINE"); p->fine_ok = !(fi != nullptr && std::atoi(fi) == 0); }
 #ifdef TTSA_PROFILE_BUILD
   { const char* dbg = std::getenv("TTSA_DEBUG"); p->debug = dbg ? std::atoi(dbg) : 0; }
 #endif
@@ -683,6 +685,17 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
   std::memset(&b->dev, 0, sizeof(b->dev));
   b->dev.B = B;
   b->dev.total_tiles = b->tile_off[B];
+  {  // fine segments (frame_kernel<..., FINE>): the first 8 frames of an utterance, then 8 - nwarm owned frames each
+    const int nwarm = (plan->cfg.win_length - 1) / plan->cfg.hop_length, own = kNF - nwarm;
+    b->fine_off.assign(B + 1, 0);
+    long long acc = 0;
+    for (int u = 0; u < B; ++u) {
+      const int T = b->T[u];
+      acc += T <= 0 ? 0 : (T <= kNF || own <= 0 ? 1 : 1 + (T - kNF + own - 1) / own);
+      b->fine_off[u + 1] = (int)std::min<long long>(acc, std::numeric_limits<int>::max());
+    }
+    b->dev.total_fine = own >= 2 ? b->fine_off[B] : 0;             // 0: the fine partition does not apply to this geometry
+  }
   if (plan->device >= 0 && plan->gl_stream) {
     b->wps_grid = plan->wps_grid;
     b->wps_win = plan->cfg.win_length;
@@ -700,7 +713,7 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
   if (plan->device >= 0) {
     DeviceGuard guard(plan->device);
     const size_t n_wps = b->wps_ok ? b->tsum.size() + b->wps_cut.size() + b->wps_u0.size() : 0;
-    const size_t n_i = (size_t)B * 2 + (size_t)(B + 1) * 2 + n_wps;     // T, wav_len, tile_off, chunk_off, [tsum, wps_cut, wps_u0]
+    const size_t n_i = (size_t)B * 2 + (size_t)(B + 1) * 3 + n_wps;     // T, wav_len, tile_off, chunk_off, [tsum, wps_cut, wps_u0], fine_off
     const size_t bytes_i = (n_i * 4 + 15) / 16 * 16;
     const size_t bytes_l = (size_t)(B + 1) * 2 * 8;
     if (cudaMalloc(&b->d_block, bytes_i + bytes_l) != cudaSuccess) { delete b; return fail(TTSA_ERR_CUDA, "cudaMalloc for batch layout failed"); }
@@ -718,6 +731,8 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
       std::memcpy(hi + 2 * B + 3 * (B + 1), b->wps_cut.data(), b->wps_cut.size() * 4);
       std::memcpy(hi + 2 * B + 3 * (B + 1) + b->wps_cut.size(), b->wps_u0.data(), b->wps_u0.size() * 4);
     }
+    const size_t fine_at = 2 * (size_t)B + 2 * (size_t)(B + 1) + n_wps;
+    std::memcpy(hi + fine_at, b->fine_off.data(), (B + 1) * 4);
     cudaError_t e = cudaMemcpy(b->d_block, h.data(), h.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(b->d_block); delete b; return fail(TTSA_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e)); }
     const long long* dl = (const long long*)b->d_block;
@@ -727,6 +742,7 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
     b->dev.T = di;
     b->dev.wav_len = di + B;
     b->dev.tile_off = di + 2 * B;
+    b->dev.fine_off = di + fine_at;
     b->d_chunk_off = di + 2 * B + (B + 1);
     if (b->wps_ok) {
       b->wps_dev.tsum = di + 2 * B + 2 * (B + 1);
@@ -811,10 +827,14 @@ static int launch_frames(const ttsa_plan* plan, const ttsa_batch* batch, int mod
                          const FrameArgs& args, cudaStream_t st, bool mom = false) {
   if (batch->dev.total_tiles == 0) return TTSA_OK;
   const int max_ctas = plan->ctas_per_sm * plan->num_sms;
-  const int grid = batch->dev.total_tiles < max_ctas ? batch->dev.total_tiles : max_ctas;
+  int grid = batch->dev.total_tiles < max_ctas ? batch->dev.total_tiles : max_ctas;
+  // small batches (the server's one sentence at a time): one CTA per fine segment, one tile phase per iteration
+  const bool fine = mode == MODE_GL_ITER && !mom && !sc && plan->fine_ok && plan->nz == 20 && batch->dev.total_fine > 0 &&
+                    batch->dev.total_fine <= max_ctas;
+  if (fine) grid = batch->dev.total_fine;
   const size_t smem = ((size_t)plan->geo.ly.sm_total + ((mode == MODE_ANALYSIS && src == OUT_FEATURES) ? plan->geo.mel_smem_floats : 0)) * 4;
   const char* err = launch_frame_kernel(mode, src, plan->nz, sc, plan->fixed_geo, mom, grid, smem, st,
-                                        plan->geo, plan->tb, batch->dev, args);
+                                        plan->geo, plan->tb, batch->dev, args, fine);
   if (err) return fail(TTSA_ERR_CUDA, "frame kernel launch (mode %d): %s", mode, err);
   return TTSA_OK;
 }
