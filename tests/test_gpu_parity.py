@@ -499,6 +499,31 @@ def test_host_pipeline_matches_oracle():
     pipe.drain()
 
 
+def test_async_audio_logger_side_stream():
+    """Training-time audio samples (train.py:225-232, 379-384) on a side stream: the caller's stream is never blocked, the
+    waveform arrives in pinned host memory and equals the oracle's inversion of the same model output."""
+    from your_voice_tts_b200 import AsyncAudioLogger
+    audio = dict(MAIN_AUDIO, griffin_lim_iters=6)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    rng = np.random.default_rng(31)
+    T_pad, T = 70, 57
+    mel_out = torch.from_numpy(rng.random((T_pad, 80)).astype(np.float32)).cuda()      # padded batch element, as the model leaves it
+    lin_out = torch.from_numpy(rng.random((T, 1025)).astype(np.float32)).cuda()
+    ang = (2 * np.pi * rng.random((T, 1025))).astype(np.float32)
+    ang_dev = torch.from_numpy(ang).cuda()
+    logger = AsyncAudioLogger(ap)
+    logger.submit("TrainAudio", mel_out, step=10, kind="mel", n_frames=T, init_angles=ang_dev)
+    mel_ref = mel_out[:T].cpu().numpy().copy()
+    mel_out.zero_()                                             # the next training step overwrites the tensor: a snapshot was taken
+    logger.submit("ValAudio", lin_out, step=11, kind="linear", init_angles=ang_dev)
+    got = logger.flush()
+    assert [(t, s) for t, s, _ in got] == [("TrainAudio", 10), ("ValAudio", 11)] and logger.poll() == []
+    yo_m = orc.inv_mel_spectrogram(mel_ref.T, init_angles=ang.T)
+    yo_l = orc.inv_spectrogram(lin_out.cpu().numpy().T, init_angles=ang.T)
+    assert got[0][2].shape == yo_m.shape and snr_db(yo_m, got[0][2]) >= GL_SNR_DB
+    assert got[1][2].shape == yo_l.shape and snr_db(yo_l, got[1][2]) >= GL_SNR_DB
+
+
 def test_feature_extraction_training_batch_cfg3():
     """BASELINE configs[2]: spectrogram + melspectrogram of a 32-utterance batch of 6 s waves in one pass."""
     ap, orc = _ap(MAIN_AUDIO), OracleAudioProcessor(**MAIN_AUDIO)

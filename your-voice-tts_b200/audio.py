@@ -201,6 +201,65 @@ class HostPipeline(object):
         self.copy.synchronize()
 
 
+class AsyncAudioLogger(object):
+    """Training-time audio samples without stalling the step (train.py:225-232, 379-384 run a CPU Griffin-Lim inside the
+    training loop).  submit() snapshots the model output that is already on the device, runs the inversion on a side
+    stream and copies the waveform to pinned host memory; the training stream never waits.  poll() hands back what has
+    finished, typically one or two steps later:
+
+        logger.submit("TrainAudio", mel_output[0], step=current_step)            # [T, num_mels] CUDA tensor
+        for tag, step, wav in logger.poll():
+            tb_logger.tb_train_audios(step, {tag: wav}, c.audio["sample_rate"])
+    """
+
+    def __init__(self, ap):
+        torch = _torch()
+        self.ap = ap
+        self.stream = torch.cuda.Stream(device=ap._dev())
+        self.pending = []
+
+    def submit(self, tag, spec_td, step=0, kind="mel", n_frames=None, seed=None, init_angles=None):
+        """spec_td: [T, num_mels] (kind "mel", inv_mel_spectrogram) or [T, num_freq] (kind "linear", inv_spectrogram),
+        normalised as the model emits it; n_frames trims the padding of a batch element."""
+        torch = _torch()
+        ap = self.ap
+        if kind not in ("mel", "linear"):
+            raise ValueError("kind must be 'mel' or 'linear'")
+        T = int(spec_td.shape[0] if n_frames is None else n_frames)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(spec_td.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)                       # the producer of spec_td has finished; nobody waits for us
+            snap = spec_td[:T].detach().to(torch.float32).contiguous().clone()
+            spec_td.record_stream(self.stream)
+            lay = ap.layout(n_frames=[T])
+            sd = int(step) if seed is None else int(seed)
+            if kind == "mel":
+                wav = ap.inv_mel_spectrogram_batch(snap, lay, init_angles=init_angles, seed=sd)
+            else:
+                wav = ap.inv_spectrogram_batch(snap, lay, init_angles=init_angles, seed=sd)
+            n = int(lay.wav_len[0])
+            host = torch.empty((n,), dtype=torch.float32).pin_memory()
+            host.copy_(wav[:n], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.pending.append((tag, int(step), host, done, wav, snap, lay))
+        return done
+
+    def poll(self):
+        """Finished items as (tag, step, numpy waveform), oldest first; never blocks."""
+        out = []
+        while self.pending and self.pending[0][3].query():
+            tag, step, host, _, _, _, _ = self.pending.pop(0)
+            out.append((tag, step, host.numpy()))
+        return out
+
+    def flush(self):
+        """Wait for everything submitted and return it (end of an epoch / of training)."""
+        self.stream.synchronize()
+        return self.poll()
+
+
 class AudioProcessor(object):
     def __init__(self,
                  sample_rate=None,
