@@ -2,7 +2,7 @@
 # weak-scaling line with the optional final NCCL gather; lines land in gpurun_out/r2_multi_N*.json
 N=$1; mkdir -p gpurun_out
 PER=$((4096 / N))
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus $N "$@" 2>gpurun_out/r2_multi_err.log | tail -1; }
+run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus $N "$@" 2>gpurun_out/r2_multi_err.log | grep "^{" | tail -1; }
 run --steps 10 --warmup 3 --no-cpu-baseline --no-extras --gather > gpurun_out/r2_multi_${N}gpu_default.json
 run --steps 3 --warmup 3 --no-cpu-baseline --no-extras --batch $PER --iters 60 > gpurun_out/r2_multi_${N}gpu_cfg5_60.json
 run --steps 3 --warmup 3 --no-cpu-baseline --no-extras --batch $PER --iters 30 > gpurun_out/r2_multi_${N}gpu_cfg5_30.json
