@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-CMD="python bench.py --no-cpu-baseline --steps 1 --warmup 3 --no-graph"
-$CMD > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gl_stream -s 20 -c 1 -o gpurun_out/r2c_wps $CMD > gpurun_out/ncu_r2c.log 2>&1
-tail -2 gpurun_out/ncu_r2c.log
-bash tools/r2_dur.sh 2>&1 | grep gl_stream
+CMD="python bench.py --no-cpu-baseline --no-extras --steps 1 --warmup 3 --no-graph"
+$CMD > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gl_stream -s 20 -c 1 -o gpurun_out/r2d_wps $CMD > gpurun_out/ncu_r2d.log 2>&1
+tail -2 gpurun_out/ncu_r2d.log

@@ -245,17 +245,6 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       const float* const pe = p ? wO1 + lane : wE + lane;          // window of the even / odd sample of pair q = lane + 32 n2
       const float* const po = p ? wE + lane : wO1 + 1 + lane;
 
-      // pull the next frame's |S| row and the input span after next towards L2 (their copies are issued later in this
-      // frame / in the next one and would otherwise pay the full HBM latency inside one transform pass)
-      if (!(kProbe & 256)) {
-        const char* nrow = reinterpret_cast<const char*>(spec_row0 + (long long)(t + 1) * kF) + 128 * lane;
-        if (t + 1 < t_end && nrow + 128 <= reinterpret_cast<const char*>(a.spec_end)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
-        const char* nspan = reinterpret_cast<const char*>(src + a0 + 2 * HOP) + 128 * lane;
-        if (t + 2 < t_end && nspan + 1024 + 128 <= reinterpret_cast<const char*>(a.wav_end)) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nspan));
-          if (lane < (4 * (WIN + 2) + 127) / 128 - 32 + 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(nspan + 4096));
-        }
-      }
       float2 R[16], I[16];
       int s_off = 0;
 #pragma unroll 1
@@ -425,22 +414,26 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       const int pn = ((t + 1) * HOP - WIN / 2) & 1;
       const int count = last ? G::kNP : (HOP + p - pn) >> 1;       // pairs [a0/2, a0(t+1)/2)
       const bool edge = last || t < G::kWarm || a0 < 0 || a0 + 2 * count > L;
-      const int b0 = base + lane;
+      // pair q = lane + 32 n of this frame lives in ring slot (base + q) mod kRH: the rows from `wrap_row` on are addressed
+      // from a second base pointer one ring length lower, so a row costs one compare and one select (immediate offsets)
+      float2* const ring_a = ring + (base + lane);
+      float2* const ring_b = ring_a - G::kRH;
+      const int wrap_row = (G::kRH - base - lane + 31) >> 5;       // first row with base + lane + 32 n >= kRH
       // one row of 32 pairs; LOAD / EMIT: 0 = no lane, 1 = per lane (q < newq / q < count), 2 = every lane
-      auto row = [&](auto nc, auto loadc, float2& v, int& sl) {
+      auto row = [&](auto nc, auto loadc, float2& v, float2*& sl) {
         constexpr int n = decltype(nc)::value, LOAD = decltype(loadc)::value;
-        sl = b0 + 32 * n; sl = sl >= G::kRH ? sl - G::kRH : sl;
+        sl = (n >= wrap_row ? ring_b : ring_a) + 32 * n;
         v = make_float2(0.0f, 0.0f);
-        if (LOAD == 2 || (LOAD == 1 && lane + 32 * n < newq)) v = ring[sl];
+        if (LOAD == 2 || (LOAD == 1 && lane + 32 * n < newq)) v = *sl;
       };
-      auto finish_row = [&](auto nc, auto emitc, auto zonec, float2 v, int sl) {
+      auto finish_row = [&](auto nc, auto emitc, auto zonec, float2 v, float2* sl) {
         constexpr int n = decltype(nc)::value, EMIT = decltype(emitc)::value;
         constexpr bool ZONE = decltype(zonec)::value;
         const float yr = (n & 1) ? R[n >> 1].y : R[n >> 1].x, yi = (n & 1) ? I[n >> 1].y : I[n >> 1].x;
         v.x = fmaf(pe[32 * n], yr, v.x);
         v.y = fmaf(-po[32 * n], yi, v.y);
         if (EMIT == 0 || (kProbe & 32)) {
-          if (32 * n + 31 < G::kNP || lane + 32 * n < G::kNP) ring[sl] = v;
+          if (32 * n + 31 < G::kNP || lane + 32 * n < G::kNP) *sl = v;
         } else {
           const int i = a0 + 2 * lane + 64 * n;                    // sample index of v.x
           float2 sc2 = make_float2(pwx[2 * lane + 64 * n + 1 - p], pwx[2 * lane + 64 * n + 2 - p]);
@@ -449,7 +442,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             sc2.y = i + 1 < zone_end ? 1.0f : sc2.y;
           }
           if (EMIT == 2 || lane + 32 * n < count) *reinterpret_cast<float2*>(dst + i) = make_float2(v.x * sc2.x, v.y * sc2.y);
-          else ring[sl] = v;
+          else *sl = v;
         }
       };
       // rows in groups: all ring loads of a group first, then the arithmetic and the stores (loads and stores of the same
@@ -460,7 +453,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
         static_for<0, 3>([&](auto gc) {
           constexpr int n0 = decltype(gc)::value * kGroup;
           float2 v[kGroup];
-          int sl[kGroup];
+          float2* sl[kGroup];
           static_for<0, kGroup>([&](auto jc) {
             constexpr int n = n0 + decltype(jc)::value;
             if constexpr (n < G::kRows) {
