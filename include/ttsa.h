@@ -138,7 +138,9 @@ int ttsa_istft(const ttsa_plan* plan, const ttsa_batch* batch, const float* stft
  *   init_angles   [sum_T, num_freq] fp32 radians, or NULL -> 2*pi*U[0,1) from a counter RNG keyed by seed
  *                 (the reference draws np.random.rand, utils/audio.py:183)
  *   sc_log_dev    NULL or [iters, n_utts, 2] fp32: (sum (|stft(y_{i-1})| - S)^2, sum S^2) per iteration/utterance
- *   workspace     >= ttsa_griffin_lim_workspace_bytes() bytes, 256-byte aligned, device memory */
+ *   workspace     >= ttsa_griffin_lim_workspace_bytes() bytes, 256-byte aligned, device memory
+ *   wav_out_dev must be 16-byte aligned (TTSA_ERR_BAD_ARG otherwise): waveform spans are read as sample pairs from
+ *   16-byte-aligned utterance slots; spectrogram rows may start at any 4-byte boundary */
 size_t ttsa_griffin_lim_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* batch);
 int ttsa_griffin_lim(const ttsa_plan* plan, const ttsa_batch* batch, const float* spec_dev, int spec_kind,
                      int iters, const float* init_angles_dev, uint64_t seed, uint32_t flags,

@@ -1030,6 +1030,9 @@ extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* ba
   if (!spec_dev || !wav_out_dev || !workspace_dev) return fail(TTSA_ERR_BAD_ARG, "null buffer");
   if (spec_kind != TTSA_SPEC_MAGNITUDE && spec_kind != TTSA_SPEC_NORM_DB) return fail(TTSA_ERR_BAD_ARG, "bad spec_kind %d", spec_kind);
   if (iters < 0) return fail(TTSA_ERR_BAD_ARG, "iters < 0");
+  // waveform spans are read as sample pairs from 16-byte-aligned utterance slots (spectrogram rows may start anywhere)
+  if (((uintptr_t)wav_out_dev | (uintptr_t)workspace_dev) & 15u)
+    return fail(TTSA_ERR_BAD_ARG, "wav_out and workspace must be 16-byte aligned");
   if (workspace_bytes < ttsa_griffin_lim_workspace_bytes(plan, batch)) return fail(TTSA_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, ttsa_griffin_lim_workspace_bytes(plan, batch));
   const bool deemph = (flags & TTSA_GL_DEEMPHASIS) != 0;
   if (deemph && plan->cfg.preemphasis == 0.0) return fail(TTSA_ERR_BAD_CONFIG, " !! Preemphasis is applied with factor 0.0. ");
