@@ -163,3 +163,20 @@ def test_strided_batch_layout():
     with pytest.raises(L.TtsaError) as ei:
         pkg.BatchLayout(plan, n_frames=[23, 50], frame_stride=48)
     assert ei.value.code == L.TTSA_ERR_BAD_ARG
+
+
+def test_load_wav_resamples_like_the_reference_call(tmp_path):
+    """utils/audio.py:235-246: load_wav(filename) asserts the configured rate; load_wav(filename, sr=...) resamples
+    (the reference through librosa.load; here a polyphase resampler -- same rate, length and spectrum)."""
+    from scipy.io import wavfile
+    sr_file, f0 = 16000, 440.0
+    t = np.arange(sr_file) / sr_file
+    wavfile.write(tmp_path / "a.wav", sr_file, (0.5 * np.sin(2 * np.pi * f0 * t) * 32767).astype(np.int16))
+    ap = AudioProcessor(verbose=False, **dict(MAIN_AUDIO, do_trim_silence=False))
+    with pytest.raises(AssertionError):
+        ap.load_wav(str(tmp_path / "a.wav"))                       # 16000 vs the configured 22050
+    x = ap.load_wav(str(tmp_path / "a.wav"), sr=22050)
+    assert abs(len(x) - 22050) <= 1
+    spec = np.abs(np.fft.rfft(x * np.hanning(len(x))))
+    assert abs(np.argmax(spec) * 22050.0 / len(x) - f0) < 2.0      # the tone is where it was
+    assert 0.45 < np.abs(x[2000:-2000]).max() < 0.55

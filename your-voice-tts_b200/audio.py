@@ -892,7 +892,15 @@ class AudioProcessor(object):
             else:
                 x = data.astype(np.float64)
         if sr is not None and sr != file_sr:
-            raise RuntimeError("resampling on load (librosa.load) is not part of this package: %s has sr %s" % (filename, file_sr))
+            # the reference resamples through librosa.load (resampy, kaiser_best); librosa is not a dependency here, so a
+            # polyphase resampler with a Kaiser window stands in for it (same rate and length, not bit-identical samples)
+            from math import gcd
+            from scipy.signal import resample_poly
+            if x.ndim > 1:
+                x = x.mean(axis=1)                                 # librosa.load(mono=True)
+            g = gcd(int(sr), int(file_sr))
+            x = resample_poly(x, int(sr) // g, int(file_sr) // g, window=("kaiser", 14.769656459379492))
+            file_sr = sr
         if self.do_trim_silence:
             try:
                 x = self.trim_silence(x)
