@@ -613,6 +613,22 @@ def test_find_endpoint_vs_oracle():
         assert np.array_equal(pcm[off[u]:off[u + 1]].cpu().numpy(), orc.save_wav_int16(w[:want[u]].astype(np.float64)))
 
 
+def test_any_size_path_is_deterministic():
+    """The any-size path (num_freq != 1025) overlap-adds in ceil(win/hop) launch phases of non-overlapping frames instead of
+    atomicAdd: repeated runs are bit-identical (and still match the oracle: test_other_transform_sizes)."""
+    audio = dict(MAIN_AUDIO, num_freq=513, frame_length_ms=40.0, frame_shift_ms=10.0, griffin_lim_iters=4)
+    ap, orc = _ap(audio), OracleAudioProcessor(**audio)
+    Ts = [70, 9, 33]
+    rng = np.random.default_rng(3)
+    spec = torch.from_numpy(rng.random((sum(Ts), 513)).astype(np.float32)).cuda()
+    ang = torch.from_numpy((2 * np.pi * rng.random((sum(Ts), 513))).astype(np.float32)).cuda()
+    lay = ap.layout(n_frames=Ts)
+    ys = [ap.inv_spectrogram_batch(spec, lay, init_angles=ang).clone() for _ in range(6)]
+    assert all(torch.equal(ys[0], y) for y in ys[1:])
+    yo = orc.inv_spectrogram(spec[:70].cpu().numpy().T, init_angles=ang[:70].cpu().numpy().T)
+    assert snr_db(yo, lay.split_wav(ys[0])[0].cpu().numpy()) >= GL_SNR_DB
+
+
 def test_save_wav_from_device_and_server_sentences(golden, tmp_path):
     """save_wav of a CUDA waveform writes the bytes scipy writes for the oracle's int16 samples; the server's
     sentence loop (server/synthesizer.py:133-162) as one batch."""

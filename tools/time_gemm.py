@@ -33,3 +33,18 @@ a.record(); runf(30); b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 30
 byt = B * (4 * wl + 4 * 1025 * 482 + 4 * 80 * 482)
 print("features 64 x 6 s: %.1f us per call = %.0f GB/s algorithmic = %.3f of the HBM roofline" % (1e3 * ms, byt / ms / 1e6, byt / ms / 1e6 / 6550.7))
+
+# any-size path (K7): num_freq 513 (n_fft 1024, hop 220, win 882), 64 utterances x 601 frames, 10 Griffin-Lim iterations
+apg = AudioProcessor(verbose=False, **dict(MAIN_AUDIO, num_freq=513, frame_length_ms=40.0, frame_shift_ms=10.0, griffin_lim_iters=10))
+Tg = 601
+layg = apg.layout(n_frames=[Tg] * B)
+specg = torch.rand((B * Tg, 513), device="cuda")
+outg = apg.inv_spectrogram_batch(specg, layg, seed=1)
+torch.cuda.synchronize()
+a.record()
+for _ in range(3):
+    outg = apg.inv_spectrogram_batch(specg, layg, seed=1, out=outg)
+b.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 3
+print("any-size path, num_freq 513, 64 x 601 frames, 10 iterations + initial synthesis + de-emphasis: %.2f ms (%.0f audio-s/s at 10 iterations)"
+      % (ms, B * 220 * (Tg - 1) / 22050 / (ms * 1e-3)))

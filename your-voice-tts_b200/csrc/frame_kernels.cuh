@@ -61,6 +61,8 @@ struct FrameArgs {
   int preemph;            // ANALYSIS: apply y[n] - p*y[n-1] while staging
   const float* wav_prev;  // GL_ITER with momentum: the estimate before wav_in; the kernel transforms wav_in - beta * wav_prev
   float beta;             //   beta = momentum / (1 + momentum)   (fast Griffin-Lim, opt-in; not in the reference)
+  int ola_phase, ola_phases;  // any-size path (generic_kernels.cuh): this launch overlap-adds the frames t = ola_phase (mod
+                          //   ola_phases); frames of one phase do not overlap, so no atomics and a fixed summation order
   int* wps_flags;         // warp-stream GL_ITER (gl_stream.cuh): per-warp "head zone stored" flag, compared with wps_epoch
   int wps_epoch;          //   (iteration number; ttsa_griffin_lim zeroes the flags once per call)
   int debug;              // profiling builds only (-DTTSA_PROFILE_BUILD + env TTSA_DEBUG): 1 = skip the frame phase,

@@ -3,7 +3,8 @@
 // frame_kernels.cuh instead).  Same reference semantics (utils/audio.py:138-201 with librosa's centred, reflect-padded,
 // Hann-windowed STFT), simplest correct mapping: one CTA per frame, a complex radix-2 transform of the whole frame in
 // shared memory (decimation in frequency forward, decimation in time inverse, so no bit-reversal pass is needed: the
-// per-bin step works on the bit-reversed positions), overlap-add by atomicAdd into a zeroed waveform followed by a
+// per-bin step works on the bit-reversed positions), overlap-add in ceil(win/hop) launch phases (frames t = p mod R of one
+// phase do not overlap: plain read-modify-write, deterministic order) into a zeroed waveform followed by a
 // window-sum-square normalisation pass.  Not tuned: it exists so that a config with another num_freq is served by
 // the CUDA path instead of TTSA_ERR_UNSUPPORTED.
 #pragma once
@@ -106,6 +107,7 @@ gen_frame_kernel(const GenGeo g, const GenTables tb, const BatchDev bd, const Fr
     }
     const int t = (int)(row - bd.frame_off[u]);
     if (t >= bd.T[u]) continue;              // padding row of a strided layout
+    if (MODE != MODE_ANALYSIS && a.ola_phases > 1 && (t % a.ola_phases) != a.ola_phase) continue;   // another launch's frame
     const int L = bd.wav_len[u];
     const long long woff = bd.wav_off[u];
     __syncthreads();                         // the previous row is done with buf / mag
@@ -210,7 +212,7 @@ gen_frame_kernel(const GenGeo g, const GenTables tb, const BatchDev bd, const Fr
       float* dst = a.wav_out + woff;
       for (int m = tid; m < g.win; m += kGenThreads) {
         const int i = t * g.hop - g.off0 + m;
-        if (i >= 0 && i < L) atomicAdd(dst + i, buf[g.lpad + m].x * inv_n * tb.win[m]);
+        if (i >= 0 && i < L) dst[i] += buf[g.lpad + m].x * inv_n * tb.win[m];   // frames of one launch phase never overlap
       }
     }
   }

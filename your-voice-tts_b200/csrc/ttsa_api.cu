@@ -278,7 +278,14 @@ static int gen_launch(const ttsa_plan* plan, const ttsa_batch* batch, int mode, 
 static int gen_synthesise(const ttsa_plan* plan, const ttsa_batch* batch, int mode, int src, const FrameArgs& a, cudaStream_t st) {
   if (batch->total_samples == 0) return TTSA_OK;
   CUDA_TRY(cudaMemsetAsync(a.wav_out, 0, (size_t)batch->total_samples * 4, st));
-  if (int rc = gen_launch(plan, batch, mode, src, a, st)) return rc;
+  // overlap-add without atomics: frames t = p (mod R), R = ceil(win / hop), do not overlap each other, so launch phase p
+  // adds them with plain read-modify-write; the phases run in stream order -> one fixed summation order per sample
+  const int phases = (plan->cfg.win_length + plan->cfg.hop_length - 1) / plan->cfg.hop_length;
+  for (int ph = 0; ph < phases; ++ph) {
+    FrameArgs b = a;
+    b.ola_phase = ph; b.ola_phases = phases;
+    if (int rc = gen_launch(plan, batch, mode, src, b, st)) return rc;
+  }
   int maxlen = 0;
   for (int v : batch->wav_len) maxlen = std::max(maxlen, v);
   if (maxlen == 0) return TTSA_OK;
