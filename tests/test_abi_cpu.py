@@ -180,3 +180,16 @@ def test_load_wav_resamples_like_the_reference_call(tmp_path):
     spec = np.abs(np.fft.rfft(x * np.hanning(len(x))))
     assert abs(np.argmax(spec) * 22050.0 / len(x) - f0) < 2.0      # the tone is where it was
     assert 0.45 < np.abs(x[2000:-2000]).max() < 0.55
+
+
+def test_pinv_follows_numpy_svd_and_moore_penrose():
+    """The pseudo-inverse comes from a one-sided Jacobi SVD of the basis itself (numpy's cut-off, rcond 1e-15), not from
+    its Gram matrix (which squares the condition number): on a heavily rank-deficient basis and on a dense one it
+    follows np.linalg.pinv (utils/audio.py:65) and satisfies the Moore-Penrose identities."""
+    for mels, fmin, fmax in ((128, 0.0, 900.0), (128, 500.0, 3000.0), (80, 0.0, 8000.0)):
+        M = lr_mel(22050, 2048, mels, fmin, fmax)
+        ap = AudioProcessor(verbose=False, **dict(MAIN_AUDIO, num_mels=mels, mel_fmin=fmin, mel_fmax=fmax))
+        P, Pref = ap._inv_mel_basis(), np.linalg.pinv(M)
+        np.testing.assert_allclose(P, Pref, atol=1e-9 * np.abs(Pref).max())
+        np.testing.assert_allclose(M @ P @ M, M, atol=1e-10 * np.abs(M).max())
+        np.testing.assert_allclose(P @ M @ P, P, atol=1e-10 * np.abs(P).max())

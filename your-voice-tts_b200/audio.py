@@ -542,10 +542,18 @@ class AudioProcessor(object):
         rem = max_len % outputs_per_step
         pad_len = max_len + (outputs_per_step - rem) if rem > 0 else max_len
         lay = self.layout(wav_lengths=lens, frame_stride=pad_len)
-        packed = torch.zeros((max(1, lay.total_samples),), dtype=torch.float32, device=dev)
-        for u, w in enumerate(wavs):
-            src = w if self._is_tensor(w) else torch.from_numpy(np.ascontiguousarray(np.asarray(w, dtype=np.float32)))
-            packed[int(lay.wav_off[u]):int(lay.wav_off[u]) + lens[u]].copy_(src.to(dev, torch.float32), non_blocking=True)
+        if all(self._is_tensor(w) and w.is_cuda for w in wavs):
+            packed = torch.zeros((max(1, lay.total_samples),), dtype=torch.float32, device=dev)
+            for u, w in enumerate(wavs):                                  # device-to-device, no host round trip
+                packed[int(lay.wav_off[u]):int(lay.wav_off[u]) + lens[u]].copy_(w.reshape(-1).to(torch.float32))
+        else:
+            # host inputs: pack once into one pinned buffer, ONE host-to-device copy for the whole batch
+            host = torch.zeros((max(1, lay.total_samples),), dtype=torch.float32).pin_memory()
+            hv = host.numpy()
+            for u, w in enumerate(wavs):
+                hv[int(lay.wav_off[u]):int(lay.wav_off[u]) + lens[u]] = (w.detach().cpu().numpy() if self._is_tensor(w)
+                                                                          else np.asarray(w, dtype=np.float32)).reshape(-1)
+            packed = host.to(dev, non_blocking=True)
         B = len(wavs)
         linear = torch.zeros((B, pad_len, self.num_freq), dtype=torch.float32, device=dev)
         mel = torch.zeros((B, pad_len, self.num_mels), dtype=torch.float32, device=dev)
@@ -556,9 +564,7 @@ class AudioProcessor(object):
         stop_max = max(T) + 1
         srem = stop_max % outputs_per_step
         stop_len = stop_max + (outputs_per_step - srem) if srem > 0 else stop_max
-        stop_targets = torch.ones((B, stop_len), dtype=torch.float32)
-        for u, t in enumerate(T):
-            stop_targets[u, :t] = 0.0
+        stop_targets = torch.from_numpy((np.arange(stop_len)[None, :] >= np.asarray(T)[:, None]).astype(np.float32))
         return linear, mel, mel_lengths, stop_targets
 
     def inv_mel_spectrogram_padded(self, mel_btd, n_frames, init_angles=None, seed=0):

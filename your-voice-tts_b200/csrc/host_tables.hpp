@@ -49,72 +49,62 @@ inline std::vector<double> mel_basis(int sr, int n_fft, int n_mels, double fmin,
   return weights;
 }
 
-// Symmetric eigen-decomposition by cyclic Jacobi: A (n x n, overwritten) -> eigenvalues on the diagonal, V columns.
-inline void jacobi_eigh(std::vector<double>& A, std::vector<double>& V, int n) {
-  V.assign((size_t)n * n, 0.0);
-  for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
+// pinv(M) for M [m x n], m <= n, through a one-sided (Hestenes) Jacobi SVD of M itself: row pairs are rotated until the
+// rows are mutually orthogonal, M = U A with orthogonal rows a_i (||a_i|| = sigma_i), so M^+ = sum_i a_i u_i^T / sigma_i^2
+// over sigma_i > rcond * sigma_max with numpy's cut-off (np.linalg.pinv: rcond = 1e-15, utils/audio.py:65).  Working on
+// M rather than on the Gram matrix M M^T keeps the condition number unsquared (near rank-deficient bases: many mels
+// with a small n_fft, a high fmin).  Returns [n x m].
+inline std::vector<double> pinv_wide(const std::vector<double>& M, int m, int n) {
+  std::vector<double> A(M), U((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) U[(size_t)i * m + i] = 1.0;
   for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0.0, diag = 0.0;
-    for (int i = 0; i < n; ++i)
-      for (int j = 0; j < n; ++j) (i == j ? diag : off) += A[(size_t)i * n + j] * A[(size_t)i * n + j];
-    if (off <= 1e-30 * diag) break;
-    for (int p = 0; p < n - 1; ++p) {
-      for (int q = p + 1; q < n; ++q) {
-        const double apq = A[(size_t)p * n + q];
-        if (apq == 0.0) continue;
-        const double app = A[(size_t)p * n + p], aqq = A[(size_t)q * n + q];
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < n; ++k) {   // columns p, q
-          const double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
-          A[(size_t)k * n + p] = c * akp - s * akq;
-          A[(size_t)k * n + q] = s * akp + c * akq;
-        }
-        for (int k = 0; k < n; ++k) {   // rows p, q
-          const double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
-          A[(size_t)p * n + k] = c * apk - s * aqk;
-          A[(size_t)q * n + k] = s * apk + c * aqk;
-        }
+    bool rotated = false;
+    for (int p = 0; p < m - 1; ++p) {
+      for (int q = p + 1; q < m; ++q) {
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        const double* ap = &A[(size_t)p * n];
+        const double* aq = &A[(size_t)q * n];
+        for (int k = 0; k < n; ++k) { alpha += ap[k] * ap[k]; beta += aq[k] * aq[k]; gamma += ap[k] * aq[k]; }
+        if (gamma == 0.0 || std::fabs(gamma) <= 1e-15 * std::sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+        double* bp = &A[(size_t)p * n];
+        double* bq = &A[(size_t)q * n];
         for (int k = 0; k < n; ++k) {
-          const double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
-          V[(size_t)k * n + p] = c * vkp - s * vkq;
-          V[(size_t)k * n + q] = s * vkp + c * vkq;
+          const double x = bp[k], y = bq[k];
+          bp[k] = c * x - sn * y;
+          bq[k] = sn * x + c * y;
+        }
+        for (int k = 0; k < m; ++k) {   // U <- U R^T: the same rotation on columns p, q
+          const double x = U[(size_t)k * m + p], y = U[(size_t)k * m + q];
+          U[(size_t)k * m + p] = c * x - sn * y;
+          U[(size_t)k * m + q] = sn * x + c * y;
         }
       }
     }
+    if (!rotated) break;
   }
-}
-
-// pinv(M) for M [m x n], m <= n:  M^+ = M^T (M M^T)^+ ; the Gram matrix is inverted through its eigen-decomposition
-// with numpy's relative cut-off on the singular values (s_i > rcond * s_max, rcond = 1e-15).  Returns [n x m].
-inline std::vector<double> pinv_wide(const std::vector<double>& M, int m, int n) {
-  std::vector<double> G((size_t)m * m, 0.0), V;
-  for (int i = 0; i < m; ++i)
-    for (int j = i; j < m; ++j) {
-      double acc = 0.0;
-      for (int k = 0; k < n; ++k) acc += M[(size_t)i * n + k] * M[(size_t)j * n + k];
-      G[(size_t)i * m + j] = G[(size_t)j * m + i] = acc;
-    }
-  jacobi_eigh(G, V, m);
-  double lmax = 0.0;
-  for (int i = 0; i < m; ++i) lmax = std::max(lmax, G[(size_t)i * m + i]);
-  // eigenvalues of the Gram matrix are squared singular values; they are only resolved to ~1e-16 * lmax
-  const double cut = std::max(1e-30, 1e-13) * lmax;
-  std::vector<double> Ginv((size_t)m * m, 0.0);
-  for (int e = 0; e < m; ++e) {
-    const double lam = G[(size_t)e * m + e];
-    if (lam <= cut) continue;
-    for (int i = 0; i < m; ++i)
-      for (int j = 0; j < m; ++j) Ginv[(size_t)i * m + j] += V[(size_t)i * m + e] * V[(size_t)j * m + e] / lam;
+  std::vector<double> sig2(m, 0.0);
+  double smax2 = 0.0;
+  for (int i = 0; i < m; ++i) {
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+    sig2[i] = acc;
+    smax2 = std::max(smax2, acc);
   }
+  const double cut2 = 1e-30 * smax2;            // sigma_i > 1e-15 * sigma_max
   std::vector<double> P((size_t)n * m, 0.0);
-  for (int k = 0; k < n; ++k)
-    for (int j = 0; j < m; ++j) {
-      double acc = 0.0;
-      for (int i = 0; i < m; ++i) acc += M[(size_t)i * n + k] * Ginv[(size_t)i * m + j];
-      P[(size_t)k * m + j] = acc;
+  for (int i = 0; i < m; ++i) {
+    if (!(sig2[i] > cut2) || sig2[i] == 0.0) continue;
+    const double inv = 1.0 / sig2[i];
+    for (int k = 0; k < n; ++k) {
+      const double a = A[(size_t)i * n + k] * inv;
+      if (a == 0.0) continue;
+      for (int j = 0; j < m; ++j) P[(size_t)k * m + j] += a * U[(size_t)j * m + i];
     }
+  }
   return P;
 }
 
