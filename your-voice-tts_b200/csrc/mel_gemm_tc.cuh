@@ -298,11 +298,14 @@ __global__ void __launch_bounds__(kM2lThreads, 1) mel_to_linear_tc_kernel(const 
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
     }
   };
-  auto epilogue = [&](int nt, long long row0) {    // drain accumulator nt & 1
-    const int b = nt & 1;
+  auto epilogue_wait = [&](int nt) {               // the MMAs of tile nt are complete: accumulator nt & 1 is readable and
+    const int b = nt & 1;                          // the B buffer nt & 1 may be refilled
     mbar_wait(bar0 + 8 * b, uses[b] & 1);
     uses[b] += 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  };
+  auto epilogue = [&](int nt, long long row0) {    // drain accumulator nt & 1 (after epilogue_wait(nt))
+    const int b = nt & 1;
     const int lane_base = (warp & 3) * 32;
     const int r = lane_base + lane;
 #pragma unroll 1
@@ -394,13 +397,14 @@ __global__ void __launch_bounds__(kM2lThreads, 1) mel_to_linear_tc_kernel(const 
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * (nt & 1)) : "memory");
       }
-      // the other B buffer was last read by the MMAs of tile nt-1, whose completion epilogue(nt-1) below waits for;
-      // tile nt-2's were waited for one iteration ago, so the buffer of tile nt+1 (= that of nt-1) is free only after
-      // that wait: issue the next copy after the epilogue's wait
-      if (nt >= 1) epilogue(nt - 1, row0);
+      // the other B buffer was last read by the MMAs of tile nt-1: once they are complete, the copy of tile nt+1 is issued
+      // into it BEFORE the epilogue work of tile nt-1, so that it streams in behind that work and the MMAs of tile nt
+      if (nt >= 1) epilogue_wait(nt - 1);
       if (nt + 1 < kM2lTiles) load_b(nt + 1);
+      if (nt >= 1) epilogue(nt - 1, row0);
     }
     __syncthreads();                                // the row stores of tile kM2lTiles-2 have read the staging buffer
+    epilogue_wait(kM2lTiles - 1);
     epilogue(kM2lTiles - 1, row0);
   }
   __syncthreads();
