@@ -221,6 +221,42 @@ def test_small_batch_fine_segments(monkeypatch):
             assert snr_db(yt, yf) >= 110.0, (Ts, u, snr_db(yt, yf))
 
 
+@pytest.mark.parametrize("sr", [22050, 16000, 24000])
+def test_stream_kernel_other_geometries_and_convergence(monkeypatch, sr):
+    """The warp-stream iteration kernel on every shipped geometry it is built for (275/1102 with an odd hop, 200/800 with an
+    even one; 300/1200 does not fit its shared-memory ring and must fall back to the tile kernel), on a ragged batch
+    forced onto a 2-CTA partition so that runs are short, cross utterance boundaries and hand zones over between CTAs;
+    normalised-dB input with spectral-convergence sums.  Against the oracle and against the tile kernel."""
+    from your_voice_tts_b200 import audio as A
+    audio = dict(MAIN_AUDIO, sample_rate=sr, griffin_lim_iters=5)
+    orc = OracleAudioProcessor(**audio)
+    Ts = [150, 90, 6, 130, 1, 7, 60, 33]
+    rng = np.random.default_rng(sr)
+    specs = [rng.random((T, 1025)).astype(np.float32) for T in Ts]
+    angs = [(2 * np.pi * rng.random((T, 1025))).astype(np.float32) for T in Ts]
+    res = {}
+    for kernel in ("stream", "tile"):
+        monkeypatch.setenv("TTSA_WPS_GRID", "2")
+        monkeypatch.setenv("TTSA_GL_KERNEL", kernel)
+        A._PLAN_CACHE.clear()
+        ap = _ap(audio)
+        lay = ap.layout(n_frames=Ts)
+        y, sc = ap.inv_spectrogram_batch(torch.from_numpy(np.concatenate(specs)).cuda(), lay,
+                                         init_angles=torch.from_numpy(np.concatenate(angs)).cuda(), return_sc=True)
+        res[kernel] = ([w.cpu().numpy().copy() for w in lay.split_wav(y)], sc.cpu().numpy().copy())
+    monkeypatch.delenv("TTSA_WPS_GRID"); monkeypatch.delenv("TTSA_GL_KERNEL")
+    A._PLAN_CACHE.clear()
+    for u, T in enumerate(Ts):
+        if T < 2:
+            continue
+        yo, sco = orc.inv_spectrogram(specs[u].T, init_angles=angs[u].T, return_sc=True)
+        ys, yt = res["stream"][0][u], res["tile"][0][u]
+        assert ys.shape == yo.shape
+        assert snr_db(yo, ys) >= GL_SNR_DB, (sr, u, snr_db(yo, ys))
+        assert snr_db(yt, ys) >= 100.0, (sr, u, snr_db(yt, ys))
+        np.testing.assert_allclose(res["stream"][1][:, u], sco, rtol=SC_RTOL)
+
+
 def test_generic_geometry_kernel_class():
     """win 1764 / hop 275 (80 ms window): more than 5 taps per hop residue and 28 non-zero packed rows -> the generic
     (NZ = 32) kernel class; and win 2048 == n_fft."""
