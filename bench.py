@@ -477,19 +477,24 @@ def main():
     if args.gather and world > 1:
         from your_voice_tts_b200.sharding import gather_packed
         lens = torch.full((B,), L_OUT, dtype=torch.int64, device=dev)
-        gather_packed(wav_out, lens)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(5):
+        for _ in range(3):                                  # communicator set-up and allocator warm-up, untimed
+            gather_packed(wav_out, lens)
+        times = []
+        for _ in range(7):
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
             blocks, totals, per_rank = gather_packed(wav_out, lens)
-        g1.record()
-        barrier()
-        t_g = torch.tensor([g0.elapsed_time(g1) / 5], device=dev, dtype=torch.float64)
-        dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
+            g1.record()
+            torch.cuda.synchronize()
+            times.append(g0.elapsed_time(g1))
+        t_g = torch.tensor(sorted(times), device=dev, dtype=torch.float64)
+        dist.all_reduce(t_g, op=dist.ReduceOp.MAX)          # element-wise max over ranks of the sorted samples
+        med = float(t_g[len(times) // 2].item())
         nbytes = int(blocks.numel()) * 4
-        line["gather"] = {"ms": float(t_g.item()), "bytes_received_per_rank": nbytes,
-                          "GBps_per_rank": nbytes / (float(t_g.item()) * 1e-3) / 1e9, "backend": "nccl",
+        line["gather"] = {"ms": med, "ms_min": float(t_g[0].item()), "ms_max": float(t_g[-1].item()), "samples": len(times),
+                          "bytes_received_per_rank": nbytes,
+                          "GBps_per_rank": nbytes / (med * 1e-3) / 1e9, "backend": "nccl",
                           "what": "sharding.gather_packed: every rank receives every rank's packed waveforms "
                                   "(2 small all_gathers for sizes + 1 all_gather_into_tensor)"}
 
