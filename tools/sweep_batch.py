@@ -7,7 +7,8 @@ from your_voice_tts_b200 import AudioProcessor, _lib as L
 ap = AudioProcessor(verbose=False, **MAIN_AUDIO)
 lib = L.load()
 print("utts  iter_ms  per64_ms  %roofline  audio-s/s(60 it)")
-for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
+BATCHES = [int(x) for x in sys.argv[1].split(',')] if len(sys.argv) > 1 else (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
+for B in BATCHES:
     lay = ap.layout(n_frames=[482] * B)
     plan = lay.plan
     S = torch.rand((lay.total_frames, 1025), device="cuda")

@@ -622,7 +622,11 @@ static bool build_wps_partition(const std::vector<int>& T, int hop, int win, int
   }
   const int G = (int)total;
   const int nw = grid * kWpsWarps;
-  if (grid <= 0 || (long long)G < (long long)nw * (2 * minrun)) return false;
+  // fewer frames per warp than this and the tile kernel serves the batch (TTSA_WPS_MINFRAMES overrides it for experiments;
+  // whatever the threshold, the checks at the end reject a partition with a run too short for the hand-over)
+  int min_frames = minrun + 1;     // measured: 32 / 40 / 48 x 482 run 0.072 / 0.087 / 0.097 ms here against 0.086 / 0.102 / 0.118 ms in the tile kernel
+  if (const char* mf = std::getenv("TTSA_WPS_MINFRAMES")) min_frames = std::max(minrun, std::atoi(mf));
+  if (grid <= 0 || (long long)G < (long long)nw * min_frames) return false;
   cut.assign(nw + 1, 0);
   for (int i = 0; i <= nw; ++i) cut[i] = (int)((long long)i * G / nw);
   // snap to utterance boundaries, keep the list monotone
