@@ -298,6 +298,10 @@ def main():
 
     # optional CUDA graph of one step (the library is capture-safe: kernel launches only)
     graph = None
+    n0 = int(lib.ttsa_launch_count())
+    step_device(1)
+    launches_per_step = int(lib.ttsa_launch_count()) - n0       # counted by the library, not assumed
+    torch.cuda.synchronize()
     if not args.no_graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -335,7 +339,6 @@ def main():
     e1.record()
     barrier()
     launches = int(lib.ttsa_launch_count()) - launches0
-    launches_per_step = 1 + 1 + ITERS + 2
     if graph is not None:
         launches = launches_per_step * args.steps          # replayed from the captured graph
     ms_total = e0.elapsed_time(e1)

@@ -257,6 +257,39 @@ def test_stream_kernel_other_geometries_and_convergence(monkeypatch, sr):
         np.testing.assert_allclose(res["stream"][1][:, u], sco, rtol=SC_RTOL)
 
 
+@pytest.mark.parametrize("sr", [22050, 16000])
+def test_stream_kernel_fused_iterations_bit_identical(monkeypatch, sr):
+    """TTSA_GL_FUSE=n runs n Griffin-Lim iterations per launch of the warp-stream kernel (neighbour-only synchronisation
+    through global flags instead of a kernel boundary, ping-pong inside the kernel).  The arithmetic and its order are the
+    same, so waveforms must be BIT-identical to one launch per iteration (the convergence sums equal up to summation order) -- on the full 148-CTA
+    partition of a long ragged batch and on a 2-CTA partition whose runs cross utterance boundaries; 7 iterations as 7, as
+    3 + 3 + 1 and as 7 x 1; repeated to catch an ordering race."""
+    from your_voice_tts_b200 import audio as A
+    audio = dict(MAIN_AUDIO, sample_rate=sr, griffin_lim_iters=7)
+    rng = np.random.default_rng(7 + sr)
+    for grid, Ts in ((None, [482] * 30 + [300, 77, 5, 1, 640]), ("2", [150, 90, 6, 130, 1, 7, 60, 33])):
+        spec = torch.from_numpy(rng.random((sum(Ts), 1025)).astype(np.float32)).cuda()
+        ang = torch.from_numpy((2 * np.pi * rng.random((sum(Ts), 1025))).astype(np.float32)).cuda()
+        res = {}
+        for fuse in ("1", "7", "3", "7"):
+            monkeypatch.setenv("TTSA_GL_FUSE", fuse)
+            if grid:
+                monkeypatch.setenv("TTSA_WPS_GRID", grid)
+            A._PLAN_CACHE.clear()
+            ap = _ap(audio)
+            lay = ap.layout(n_frames=Ts)
+            y, sc = ap.inv_spectrogram_batch(spec, lay, init_angles=ang, return_sc=True)
+            out = (y.cpu().numpy().copy(), sc.cpu().numpy().copy())
+            if "1" in res:
+                assert np.array_equal(out[0], res["1"][0]), (sr, grid, fuse)
+                np.testing.assert_allclose(out[1], res["1"][1], rtol=1e-5)     # atomicAdd over warps: order varies
+            res[fuse] = out
+        assert np.isfinite(res["1"][0]).all() and float(np.abs(res["1"][0]).max()) > 0
+    monkeypatch.delenv("TTSA_GL_FUSE")
+    monkeypatch.delenv("TTSA_WPS_GRID", raising=False)
+    A._PLAN_CACHE.clear()
+
+
 def test_generic_geometry_kernel_class():
     """win 1764 / hop 275 (80 ms window): more than 5 taps per hop residue and 28 non-zero packed rows -> the generic
     (NZ = 32) kernel class; and win 2048 == n_fft."""

@@ -65,6 +65,11 @@ struct FrameArgs {
                           //   ola_phases); frames of one phase do not overlap, so no atomics and a fixed summation order
   int* wps_flags;         // warp-stream GL_ITER (gl_stream.cuh): per-warp "head zone stored" flag, compared with wps_epoch
   int wps_epoch;          //   (iteration number; ttsa_griffin_lim zeroes the flags once per call)
+  int* wps_done;          //   per-warp "iteration complete" flag (same epochs) for launches that run several iterations
+  int wps_iters;          //   iterations this launch runs: iteration j reads wav_in / wav_out for even / odd j, writes the other
+#ifdef TTSA_WPS_TRACE
+  unsigned long long* wps_trace;   // [warps][64 iterations][8 stamps] (experiment builds)
+#endif
   int debug;              // profiling builds only (-DTTSA_PROFILE_BUILD + env TTSA_DEBUG): 1 = skip the frame phase,
                           // 2 = skip overlap-add + staging work; the shipped library compiles these branches out
 };

@@ -78,12 +78,51 @@ __device__ __forceinline__ int span_to_smem_bulk_n(float* dst, const float* ptr,
   }
   return span_to_smem_async(dst, ptr, N, lo, hi, lane);
 }
+// An input span that lies inside its utterance's slot of the packed waveform buffer (slots start 16-byte aligned and are
+// padded to whole 16-byte chunks, so the enclosing aligned range is inside the slot as well): always one bulk copy.
+template <int N>
+__device__ __forceinline__ int span_to_smem_bulk_inside(float* dst, const float* ptr, int lane, unsigned mbar) {
+  const int off = (int)((reinterpret_cast<unsigned long long>(ptr) >> 2) & 3ull);
+  if (lane == 0) {
+    const unsigned bytes = (unsigned)((off + N + 3) >> 2) << 4;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(ptr - off), "r"(bytes), "r"(mbar) : "memory");
+  }
+  return off;
+}
+__device__ __forceinline__ float ld_relaxed_gpu_f32(const float* p) {      // coherent at gpu scope (not served by a stale L1 line)
+  float v;
+  asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
   unsigned done = 0;
   while (!done) {
     asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
                  : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
   }
+}
+
+__device__ __forceinline__ int ld_relaxed_gpu_s32(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Wait until *p >= v (flags only grow).  One lane polls with an acquire load (every acquire invalidates the SM's L1, so
+// not 32 of them per poll); the warp barrier extends the ordering to the other lanes, whose reads of the published data
+// are L2 loads (ld.relaxed.gpu) or bulk copies issued by the polling lane.
+__device__ __forceinline__ void wait_flag_ge(const int* p, int v, bool poller) {
+  if (poller) while (ld_acquire_gpu(p) < v) __nanosleep(64);
+  __syncwarp();
+}
+// Publish flag *p = v after everything the warp wrote: one fence per lane, then a relaxed store by one lane (fence +
+// relaxed store is the release pattern; st.release would add a second fence, __threadfence() a sequentially consistent one).
+__device__ __forceinline__ void publish_flag(int* p, int v, bool writer) {
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  __syncwarp();
+  if (writer) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <int HOP, int WIN>
@@ -121,6 +160,14 @@ struct WpsGeo {
   static constexpr int sm_total = sm_mbar + 4 + 4 * kWpsWarps;   // + two mbarriers per warp (|S| row, input span)
   static constexpr bool kFits = sm_total * 4 <= 227 * 1024;
 };
+
+// -DTTSA_WPS_TRACE (experiment builds, tools/wps_trace.py): per-warp global-timer stamps of every iteration's phases
+#ifdef TTSA_WPS_TRACE
+#define WPS_STAMP(k) do { if (l0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    a.wps_trace[((size_t)wi * 64 + (it & 63)) * 8 + (k)] = t_; } } while (0)
+#else
+#define WPS_STAMP(k) do {} while (0)
+#endif
 
 template <int SRC, bool SC, int HOP, int WIN>
 __global__ void __launch_bounds__(kWpsThreads, 1)
@@ -177,7 +224,6 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
   }
   const int wi = blockIdx.x * kWpsWarps + warp;
   const int fa = wp.cut[wi], fb = wp.cut[wi + 1];
-  int u = wp.u0[wi];                                               // utterance of frame fa (host-built)
   __syncthreads();                                                 // the mbarrier is initialised for everyone
   {
     unsigned done = 0;
@@ -193,6 +239,32 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
   unsigned ph_s = 0, ph_x = 0;
   const int partner = (32 - lane) & 31;
   const bool l0 = lane == 0;
+  // ---- iterations of this launch.  Iteration `it` reads the waveform iteration it - 1 wrote (ping-pong between wav_in and
+  // wav_out).  A kernel boundary between iterations is NOT needed: a warp's input spans cover its own output region plus
+  // the head zone of the next run (which it finishes itself), and the only samples somebody else writes into its region are
+  // its head zone, finished by the owner of the frames before the cut at the end of THAT warp's run.  So a warp whose range
+  // starts inside an utterance waits for the previous warp's "iteration done" flag (release / acquire at gpu scope) and
+  // every other warp starts at once.  The same wait orders the write-after-read on the ping-pong buffers (the previous
+  // warp's last frames read into this warp's region).  SMs therefore drift apart by whole frames between iterations: a
+  // 14-frame run no longer makes 2 367 other warps wait at a kernel boundary, and launch / prologue / drain are paid once.
+  const int n_it = a.wps_iters;
+#pragma unroll 1
+  for (int it = 0; it < n_it; ++it) {
+  const int epoch = a.wps_epoch + it;
+  int u = wp.u0[wi];                                               // utterance of frame fa (host-built)
+  WPS_STAMP(0);
+  if (it > 0 && fa < fb) {
+    if (wp.tsum[u] < fa) {                                         // the range starts inside utterance u
+      int pw = wi - 1;
+      while (wp.cut[pw + 1] == wp.cut[pw]) --pw;                   // some earlier warp owns frame fa - 1
+      wait_flag_ge(a.wps_done + pw, epoch - 1, l0);
+    }
+    // the bulk copies below read (async proxy) what ordinary stores of the previous iteration wrote
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+  }
+  WPS_STAMP(1);
+  const float* const wav_rd = (it & 1) ? a.wav_out : a.wav_in;
+  float* const wav_wr = (it & 1) ? const_cast<float*>(a.wav_in) : a.wav_out;
   int f = fa;
   while (f < fb) {
     while (wp.tsum[u + 1] <= f) ++u;                               // skips empty utterances
@@ -204,8 +276,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
     const int L = bd.wav_len[u];
     if (L <= 0) continue;
     const long long woff = bd.wav_off[u];
-    const float* __restrict__ src = a.wav_in + woff;
-    float* __restrict__ dst = a.wav_out + woff;
+    const float* __restrict__ src = wav_rd + woff;
+    float* __restrict__ dst = wav_wr + woff;
     const float* spec_row0 = a.spec + bd.frame_off[u] * kF;
 
     // a run that starts inside the utterance leaves its first kZone samples as raw partial sums; the owner of the
@@ -220,15 +292,54 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       const int a0 = s0 - (s0 & 1);
       return a0 >= 0 && a0 + WIN + 2 <= L;
     };
+    const bool edge_async = L >= 2 * (WIN + 2);                    // one fold of the reflection per span, source inside the copy
+    // a frame whose span was copied by the edge path: fill the samples outside [0, L) from their mirror images
+    auto fill_reflected = [&](int a0, int x_off) {
+      const int A = a0 - x_off;
+      const int c_lo = max(A, 0), c_hi = min(a0 + WIN + 2, L);
+      // edge_async: one fold.  Sample idx < 0 mirrors to -idx, idx >= L to 2 (L - 1) - idx; a mirror image outside the copy
+      // belongs to a zero-tap padding element of the aligned frame
+#pragma unroll 1
+      for (int idx = a0 + lane; idx < 0; idx += 32) buf[idx - A] = (-idx < c_hi) ? buf[-idx - A] : 0.0f;
+#pragma unroll 1
+      for (int idx = L + lane; idx < a0 + WIN + 2; idx += 32) {
+        const int r = 2 * (L - 1) - idx;
+        buf[idx - A] = (r >= c_lo) ? buf[r - A] : 0.0f;
+      }
+      __syncwarp();
+    };
     bool x_bulk = false;
     auto span_issue = [&](int t) {                                 // returns the landing offset (0 or 2)
       const int s0 = t * HOP - WIN / 2;
       const int a0 = s0 - (s0 & 1);
-      if (span_fast(t)) return span_to_smem_bulk_n<WIN + 2>(buf, (kProbe & 4096) ? src + 4096 + (a0 & 2) + 64 * warp : src + a0, a.wav_in, a.wav_end, lane, mbar_x, x_bulk);
+      if (span_fast(t)) { x_bulk = true; return span_to_smem_bulk_inside<WIN + 2>(buf, src + a0, lane, mbar_x); }
+      if (edge_async) {
+        // the first and last frames of an utterance (np.pad(..., mode='reflect')): the part of the span that exists, from 8
+        // samples before the frame (a reflected tap of the last frame can point just below it), by one bulk copy; the
+        // reflected part is filled in from shared memory when the frame is consumed (fill_reflected)
+        const int A = (a0 - 8) & ~3;                               // sample that lands at buf[0]
+        if (lane == 0) {
+          const int c_lo = max(A, 0), c_hi = (min(a0 + WIN + 2, L) + 3) & ~3;
+          const unsigned bytes = (unsigned)(c_hi - c_lo) << 2;
+          const unsigned d = (unsigned)__cvta_generic_to_shared(buf + (c_lo - A));
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_x), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(d), "l"(src + c_lo), "r"(bytes), "r"(mbar_x) : "memory");
+        }
+        x_bulk = true;
+        return a0 - A;
+      }
       x_bulk = false;
-      // the utterance's first and last frames: np.pad(..., mode='reflect') as an index map, 4-byte asynchronous copies
-#pragma unroll 4
-      for (int m = lane; m < WIN + 2; m += 32) cp_async4(buf + m, src + reflect_index(a0 + m, L));
+      // short utterances (several folds of the reflection inside one span).  Loads at gpu scope: with
+      // several iterations per launch the same address is re-read after other SMs rewrote it, so no L1-allocating copy
+#pragma unroll 1
+      for (int m0 = lane; m0 < WIN + 2; m0 += 32 * 6) {
+        float v[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { const int m = m0 + 32 * k; v[k] = m < WIN + 2 ? ld_relaxed_gpu_f32(src + reflect_index(a0 + m, L)) : 0.0f; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { const int m = m0 + 32 * k; if (m < WIN + 2) buf[m] = v[k]; }
+      }
       return 0;
     };
     int x_off = 0;
@@ -255,6 +366,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
           } else if (x_bulk) { mbar_wait(mbar_x, ph_x); ph_x ^= 1u; x_bulk = false; }
           else cp_async_wait_all();
           __syncwarp();
+          if (edge_async && !span_fast(t)) fill_reflected(a0, x_off);
           const float2* const xp = reinterpret_cast<const float2*>(buf + x_off) + lane;
 #pragma unroll
           for (int m = 0; m < 16; ++m) {
@@ -496,12 +608,11 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       newq = G::kNP - count;
       base += count; base = base >= G::kRH ? base - G::kRH : base;
       if (zone_pending && a0 + 2 * count >= zone_end) {            // the head zone is stored: the owner of the frames before
-        __threadfence();                                           // the cut may finish it (release at gpu scope)
-        __syncwarp();
-        if (l0) st_release_gpu(a.wps_flags + wi, a.wps_epoch);
+        publish_flag(a.wps_flags + wi, epoch, l0);                 // the cut may finish it (release at gpu scope)
         zone_pending = false;
       }
     }  // frames of the run
+    WPS_STAMP(2);
 
     if constexpr (SC) {
 #pragma unroll
@@ -510,8 +621,9 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
         sc_den += __shfl_xor_sync(0xffffffffu, sc_den, o);
       }
       if (lane == 0) {
-        atomicAdd(a.sc_acc + 2 * u, sc_num);
-        atomicAdd(a.sc_acc + 2 * u + 1, sc_den);
+        float* const acc = a.sc_acc + 2 * ((size_t)it * bd.B + u);     // [iteration][utterance][num, den]
+        atomicAdd(acc, sc_num);
+        atomicAdd(acc + 1, sc_den);
       }
     }
     // A run that ends inside the utterance holds the partial sums of the next run's head zone in its ring: wait until
@@ -525,7 +637,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       constexpr int kZoneIters = ((G::kZone + 3) / 2 + 31) / 32;
       int nx = wi + 1;
       while (wp.cut[nx + 1] == wp.cut[nx]) ++nx;                   // the cut list ends at the total frame count > cut[nx]
-      while (ld_acquire_gpu(a.wps_flags + nx) != a.wps_epoch) __nanosleep(64);
+      wait_flag_ge(a.wps_flags + nx, epoch, l0);
+      WPS_STAMP(3);
       const bool all_frames = t_end >= G::kWarm && t_end + G::kWarm < T;
       float2 v[kZoneIters], o[kZoneIters];
 #pragma unroll
@@ -558,6 +671,12 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       }
     }
   }  // runs
+  WPS_STAMP(4);
+  if (n_it > 1 && fa < fb) {                                       // this warp's part of iteration `it` is complete and visible
+    publish_flag(a.wps_done + wi, epoch, l0);
+  }
+  WPS_STAMP(5);
+  }  // iterations
 }
 
 }  // namespace ttsa

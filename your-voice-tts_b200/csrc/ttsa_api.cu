@@ -610,6 +610,16 @@ extern "C" int ttsa_plan_inv_mel_basis(const ttsa_plan* plan, double* host_out) 
 // with its longest run): cuts start evenly spaced, cuts too close to a boundary snap onto it, and the cuts between two
 // consecutive boundary cuts of the same utterance are then re-spaced evenly, so run lengths differ by at most one frame
 // wherever utterances are longer than a run.  Returns false when the batch is too small (the tile kernel serves it).
+// extra cost of an utterance's first (which = 0) / last (1) run in frame times; TTSA_WPS_EDGE="e0,e1" overrides (experiments)
+static double wps_edge_cost(int which) {
+  double e[2] = {0.0, 0.0};   // measured at 64 x 482: (0, 0) 0.1280 ms, (1, 1.5) 0.1287 ms, (2, 2.5) 0.1296 ms per launch
+  if (const char* s = std::getenv("TTSA_WPS_EDGE")) {
+    double x0, x1;
+    if (std::sscanf(s, "%lf,%lf", &x0, &x1) == 2 && x0 >= 0 && x1 >= 0 && x0 < 8 && x1 < 8) { e[0] = x0; e[1] = x1; }
+  }
+  return e[which];
+}
+
 static bool build_wps_partition(const std::vector<int>& T, int hop, int win, int grid, std::vector<int>& tsum, std::vector<int>& cut) {
   const int B = (int)T.size();
   const int warm = (win - 1) / hop, minrun = warm + 1;
@@ -653,8 +663,19 @@ static bool build_wps_partition(const std::vector<int>& T, int hop, int win, int
     if (n > 1 && b > a) {
       int ua = 0;
       { int lo = 0, hi = B; while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tsum[mid] <= a) lo = mid; else hi = mid; } ua = lo; }
-      if (b <= tsum[ua + 1] && (long long)(b - a) >= (long long)n * minrun)
-        for (int i = ia + 1; i < ib; ++i) cut[i] = a + (int)((long long)(i - ia) * (b - a) / n);
+      if (b <= tsum[ua + 1] && (long long)(b - a) >= (long long)n * minrun) {
+        // The runs that hold an utterance's first frames (reflected spans, window sums over the frames that exist) and its
+        // last ones (the same, plus the flush of the whole window) cost somewhat more than an interior run of the same
+        // length; e0 / e1 (in frame times, TTSA_WPS_EDGE) shorten them.  With 30 848 frames over 2 368 warps some run has 14
+        // frames whatever the weights, and that run paces the launch: the weights made no measurable difference (default 0).
+        const double e0 = (a == tsum[ua]) ? wps_edge_cost(0) : 0.0, e1 = (b == tsum[ua + 1]) ? wps_edge_cost(1) : 0.0;
+        const double c = ((double)(b - a) + e0 + e1) / n;            // cost per run, in frames
+        if (c - e0 >= minrun && c - e1 >= minrun && c >= minrun + 1) {
+          for (int i = ia + 1; i < ib; ++i) cut[i] = a + (int)std::floor((double)(i - ia) * c - e0 + 0.5);
+        } else {
+          for (int i = ia + 1; i < ib; ++i) cut[i] = a + (int)((long long)(i - ia) * (b - a) / n);
+        }
+      }
     }
     ia = ib;
   }
@@ -890,7 +911,11 @@ extern "C" size_t ttsa_deemphasis_workspace_bytes(const ttsa_plan* plan, const t
 }
 
 static size_t wps_flag_bytes(const ttsa_batch* batch) {
-  return batch->wps_ok ? ((size_t)batch->wps_grid * kWpsWarps * 4 + 255) / 256 * 256 : 0;
+  size_t n = batch->wps_ok ? 2 * (((size_t)batch->wps_grid * kWpsWarps * 4 + 255) / 256 * 256) : 0;   // head-zone flags, done flags
+#ifdef TTSA_WPS_TRACE
+  if (batch->wps_ok) n += (size_t)batch->wps_grid * kWpsWarps * 64 * 8 * 8;                          // stamps, at the very end
+#endif
+  return n;
 }
 
 extern "C" size_t ttsa_griffin_lim_workspace_bytes(const ttsa_plan* plan, const ttsa_batch* batch) {
@@ -1094,6 +1119,13 @@ extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* ba
   a.spec = spec_dev; a.spec_end = spec_dev + (size_t)batch->total_frames * kF; a.rows_total = batch->total_frames;
   a.angles = init_angles_dev; a.seed = seed; a.wav_out = bufs[0];
   if (int rc = launch_frames(plan, batch, MODE_SYNTH, spec_kind, false, a, st)) return rc;
+  // The warp-stream kernel can run several iterations in ONE launch (neighbour-only synchronisation between iterations
+  // through global flags, gl_stream.cuh): TTSA_GL_FUSE=n runs up to n iterations per launch.  Measured at 64 x 482
+  // (DESIGN.md, K3 "fused iterations"): 0.1416 ms per iteration fused against 0.1285 ms with one launch per iteration --
+  // the hand-over at a run's end (wait, finish the next run's head zone, publish: 12 us) is on every warp's cycle when
+  // iterations are chained, while a kernel boundary overlaps it with the other warps' last frames -- so the default is 1.
+  int fuse = 1;
+  if (const char* fz = std::getenv("TTSA_GL_FUSE")) fuse = std::max(1, std::atoi(fz));
   for (int i = 1; i <= iters; ++i) {
     FrameArgs b{};
     b.spec = spec_dev; b.spec_end = spec_dev + (size_t)batch->total_frames * kF;
@@ -1105,6 +1137,12 @@ extern "C" int ttsa_griffin_lim_fast(const ttsa_plan* plan, const ttsa_batch* ba
     b.sc_acc = sc_log_dev ? sc_log_dev + (size_t)(i - 1) * batch->B * 2 : nullptr;
     if (!mom_i && use_stream) {
       b.wps_flags = wps_flags; b.wps_epoch = i;
+      b.wps_done = wps_flags + ((size_t)batch->wps_grid * kWpsWarps * 4 + 255) / 256 * 64;
+#ifdef TTSA_WPS_TRACE
+      b.wps_trace = (unsigned long long*)((char*)wps_flags + wps_flag_bytes(batch) - (size_t)batch->wps_grid * kWpsWarps * 64 * 8 * 8);
+#endif
+      b.wps_iters = mom ? 1 : std::min(fuse, iters - i + 1);  // nb == 2 without momentum: the kernel's ping-pong is bufs[]'s
+      i += b.wps_iters - 1;
       const char* err = launch_gl_stream(spec_kind, sc_log_dev != nullptr, plan->cfg.hop_length, plan->cfg.win_length, batch->wps_grid,
                                          st, plan->geo, plan->tb, batch->dev, batch->wps_dev, b);
       if (err) return fail(TTSA_ERR_CUDA, "Griffin-Lim stream kernel launch: %s", err);
