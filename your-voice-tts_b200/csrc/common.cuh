@@ -85,7 +85,7 @@ struct Tables {
   const float2* pw2;     // [hop]    (pw[r], pw[(r + 1) % hop]) / n_fft   (sample pairs of the warp-stream Griffin-Lim kernel)
   const float* edge_head;   // [max(0, warm*hop - win/2)]  1 / (n_fft wss) of an utterance's first samples (frames before 0 missing)
   const float* edge_tail;   // [max(0, win/2 - hop)]       the same for its last samples (frame T missing); gl_stream.cuh
-  const float* wps_image;   // table image of the warp-stream Griffin-Lim kernel (gl_stream.cuh, WpsGeo): tw4 | g4 | wE | wO1 | pwx
+  const float* wps_image;   // table image of the warp-stream Griffin-Lim kernel (gl_stream.cuh, WpsGeo): tw4 | g4 | wA | wB | pwx
   const float* smem_image;  // [Layout::image_floats]  wE2 | wO2 | pw / n_fft | signed synthesis window | tw4 | g4, laid out
                             // exactly as the kernels keep them in shared memory (one bulk copy per CTA)
   // sparse mel basis (CSR over mel rows; each row is one contiguous run of bins)
@@ -113,6 +113,7 @@ struct BatchDev {
 #ifndef TTSA_WPS_WARPS
 #define TTSA_WPS_WARPS 16
 #endif
+constexpr int kWpsWinStride = 20;           // floats per lane row of the warp-stream kernel's window tables (>= rows of a frame; stride / 4 odd)
 constexpr int kWpsWarps = TTSA_WPS_WARPS;   // warps per CTA (one CTA per SM) of the warp-stream Griffin-Lim kernel
 
 // Work partition of the warp-stream Griffin-Lim kernel (gl_stream.cuh), built by the host with the batch.

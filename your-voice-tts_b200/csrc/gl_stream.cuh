@@ -152,10 +152,12 @@ struct WpsGeo {
   static constexpr int sm_img = kWpsWarps * kWarpFloats;
   static constexpr int sm_tw = sm_img;                           // float4[16][32]
   static constexpr int sm_g = sm_tw + 2048;                      // float4[8][32]
-  static constexpr int sm_wE = sm_g + 1024;                      // [kRH]      w[2q]
-  static constexpr int sm_wO1 = sm_wE + kRH;                     // [kRH + 4]  w[2(q-1)+1], entry 0 = 0
-  static constexpr int sm_pwx = sm_wO1 + kRH + 4;                // [kPwx]     pwx[j] = 1 / (n_fft wss[(j - 1) mod HOP])
-  static constexpr int image_floats = 2048 + 1024 + 2 * kRH + 4 + kPwx;
+  static constexpr int kWS = kWpsWinStride;                      // window taps per lane: pair q = lane + 32 n at [lane][n]
+  static_assert(kRows <= kWS && (kWS / 4) % 2 == 1, "lane rows of the window tables: 16-byte loads without bank conflicts");
+  static constexpr int sm_wA = sm_g + 1024;                      // [32][kWS]  w[2q]
+  static constexpr int sm_wB = sm_wA + 32 * kWS;                 // [33][kWS]  row lane + 1: w[2q+1]; row lane: w[2(q-1)+1] = w[2q-1]
+  static constexpr int sm_pwx = sm_wB + 33 * kWS;                // [kPwx]     pwx[j] = 1 / (n_fft wss[(j - 1) mod HOP])
+  static constexpr int image_floats = 2048 + 1024 + 65 * kWS + kPwx;
   static constexpr int sm_mbar = sm_img + image_floats;          // 8-byte aligned (image_floats is a multiple of 4)
   static constexpr int sm_total = sm_mbar + 4 + 4 * kWpsWarps;   // + two mbarriers per warp (|S| row, input span)
   static constexpr bool kFits = sm_total * 4 <= 227 * 1024;
@@ -183,8 +185,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
   float2* const ring = reinterpret_cast<float2*>(buf + kBufFloats);
   const float4* const tw4 = reinterpret_cast<const float4*>(smem + G::sm_tw);
   const float4* const g4 = reinterpret_cast<const float4*>(smem + G::sm_g);
-  const float* const wE = smem + G::sm_wE;
-  const float* const wO1 = smem + G::sm_wO1;
+  const float* const wA = smem + G::sm_wA;
+  const float* const wB = smem + G::sm_wB;
   const float* const pwx = smem + G::sm_pwx;
 
   // 1 / (n_fft * window sum of squares) at sample i of an utterance with T frames, over the frames that exist
@@ -195,7 +197,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
     for (int tt = tq; tt >= 0 && tt > tq - (G::kWarm + 1); --tt) {
       const int mtap = i - (tt * HOP - WIN / 2);
       if (tt < T && mtap >= 0 && mtap < WIN) {
-        const float wv = (mtap & 1) ? wO1[(mtap >> 1) + 1] : wE[mtap >> 1];
+        const int q = mtap >> 1;
+        const float wv = (mtap & 1) ? wB[((q & 31) + 1) * G::kWS + (q >> 5)] : wA[(q & 31) * G::kWS + (q >> 5)];
         ws = fmaf(wv, wv, ws);
       }
     }
@@ -353,8 +356,9 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       const int s0 = t * HOP - WIN / 2;
       const int p = s0 & 1;
       const int a0 = s0 - p;
-      const float* const pe = p ? wO1 + lane : wE + lane;          // window of the even / odd sample of pair q = lane + 32 n2
-      const float* const po = p ? wE + lane : wO1 + 1 + lane;
+      // window of the even / odd sample of pair q = lane + 32 n: pe[n], po[n] (an odd frame starts one sample early)
+      const float* const pe = (p ? wB : wA) + lane * G::kWS;
+      const float* const po = (p ? wA : wB + G::kWS) + lane * G::kWS;
 
       float2 R[16], I[16];
       int s_off = 0;
@@ -375,9 +379,12 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
               // another utterance's bad spectrum must not leak into this one)
               float2 xa = xp[64 * m];
               if (64 * m + 31 >= WIN / 2 && lane + 64 * m >= WIN / 2 + p) xa = make_float2(0.0f, 0.0f);
-              float2 xb = make_float2(0.0f, 0.0f), we = make_float2(pe[64 * m], 0.0f), wo = make_float2(po[64 * m], 0.0f);
+              // taps of rows 2m, 2m + 1 by one 8-byte load per table (adjacent ones merge into 16-byte loads)
+              float2 xb = make_float2(0.0f, 0.0f);
+              const float2 we = (kProbe & 32768) ? make_float2(0.5f + 1e-3f * m, 0.3f) : *reinterpret_cast<const float2*>(pe + 2 * m);
+              const float2 wo = (kProbe & 32768) ? make_float2(0.4f, 0.2f + 1e-3f * m) : *reinterpret_cast<const float2*>(po + 2 * m);
               if (2 * m + 1 < G::kRows) {
-                xb = xp[64 * m + 32]; we.y = pe[64 * m + 32]; wo.y = po[64 * m + 32];
+                xb = xp[64 * m + 32];
                 if (64 * m + 63 >= WIN / 2 && lane + 64 * m + 32 >= WIN / 2 + p) xb = make_float2(0.0f, 0.0f);
               }
               R[m] = __fmul2_rn(make_float2(xa.x, xb.x), we);
@@ -409,7 +416,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
           static_for<0, 8>([&](auto mc) {
             constexpr int m = decltype(mc)::value;
             const int k0 = 64 * m + lane;
-            const float4 gq = g4[m * 32 + lane];
+            const float4 gq = (kProbe & 16384) ? make_float4(0.7f, 0.6f, 0.5f + 1e-3f * m, 0.4f) : g4[m * 32 + lane];
             const float2 GX = make_float2(gq.x, gq.y), GY = make_float2(gq.z, gq.w);
             const float2 Sk = make_float2(spec_to_mag<SRC>(srow[k0], g), spec_to_mag<SRC>(srow[k0 + 32], g));
             const float2 Sp = make_float2(spec_to_mag<SRC>(srow[1024 - k0], g), spec_to_mag<SRC>(srow[992 - k0], g));
@@ -483,7 +490,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
           if (pass == 0) {
 #pragma unroll
             for (int m = 0; m < 16 && !(kProbe & 2); ++m) {       // times W_1024^(lane * k2), k2 = 2m, 2m+1
-              const float4 w = tw4[m * 32 + lane];
+              const float4 w = (kProbe & 8192) ? make_float4(0.7f, 0.6f, 0.5f + 1e-3f * m, 0.4f) : tw4[m * 32 + lane];
               const float2 WR = make_float2(w.x, w.y), WI = make_float2(w.z, w.w);
               const float2 nr = __ffma2_rn(R[m], WR, neg2(__fmul2_rn(I[m], WI)));
               I[m] = __ffma2_rn(R[m], WI, __fmul2_rn(I[m], WR));
@@ -538,12 +545,12 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
         v = make_float2(0.0f, 0.0f);
         if (LOAD == 2 || (LOAD == 1 && lane + 32 * n < newq)) v = *sl;
       };
-      auto finish_row = [&](auto nc, auto emitc, auto zonec, float2 v, float2* sl) {
+      auto finish_row = [&](auto nc, auto emitc, auto zonec, float2 v, float2* sl, float tap_e, float tap_o) {
         constexpr int n = decltype(nc)::value, EMIT = decltype(emitc)::value;
         constexpr bool ZONE = decltype(zonec)::value;
         const float yr = (n & 1) ? R[n >> 1].y : R[n >> 1].x, yi = (n & 1) ? I[n >> 1].y : I[n >> 1].x;
-        v.x = fmaf(pe[32 * n], yr, v.x);
-        v.y = fmaf(-po[32 * n], yi, v.y);
+        v.x = fmaf((kProbe & 32768) ? 0.5f + 1e-3f * n : tap_e, yr, v.x);
+        v.y = fmaf((kProbe & 32768) ? -0.4f : -tap_o, yi, v.y);
         if (EMIT == 0 || (kProbe & 32)) {
           if (32 * n + 31 < G::kNP || lane + 32 * n < G::kNP) *sl = v;
         } else {
@@ -561,11 +568,23 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       // array cannot be reordered by the compiler; a load-modify-store chain per row would expose the latency 18 times)
       auto pass_rows = [&](auto zonec, auto edgec) {
         constexpr bool ZONE = decltype(zonec)::value, EDGE = decltype(edgec)::value;
-        constexpr int kGroup = (G::kRows + 2) / 3;
-        static_for<0, 3>([&](auto gc) {
+        constexpr int kGroup = 8;                                  // two 16-byte loads of window taps per table and group
+        static_for<0, (G::kRows + kGroup - 1) / kGroup>([&](auto gc) {
           constexpr int n0 = decltype(gc)::value * kGroup;
           float2 v[kGroup];
           float2* sl[kGroup];
+          float tap_e[kGroup], tap_o[kGroup];
+          static_for<0, kGroup / 4>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            if constexpr (n0 + 4 * j < G::kRows && !(kProbe & 32768)) {
+              const float4 e4 = *reinterpret_cast<const float4*>(pe + n0 + 4 * j), o4 = *reinterpret_cast<const float4*>(po + n0 + 4 * j);
+              tap_e[4 * j] = e4.x; tap_e[4 * j + 1] = e4.y; tap_e[4 * j + 2] = e4.z; tap_e[4 * j + 3] = e4.w;
+              tap_o[4 * j] = o4.x; tap_o[4 * j + 1] = o4.y; tap_o[4 * j + 2] = o4.z; tap_o[4 * j + 3] = o4.w;
+            } else {
+              tap_e[4 * j] = tap_e[4 * j + 1] = tap_e[4 * j + 2] = tap_e[4 * j + 3] = 0.0f;
+              tap_o[4 * j] = tap_o[4 * j + 1] = tap_o[4 * j + 2] = tap_o[4 * j + 3] = 0.0f;
+            }
+          });
           static_for<0, kGroup>([&](auto jc) {
             constexpr int n = n0 + decltype(jc)::value;
             if constexpr (n < G::kRows) {
@@ -578,7 +597,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
             constexpr int n = n0 + decltype(jc)::value;
             if constexpr (n < G::kRows) {
               constexpr int EMIT = EDGE ? 0 : (32 * n + 31 < G::kCntMin ? 2 : (32 * n < G::kCntMax ? 1 : 0));
-              finish_row(IntC<n>{}, IntC<EMIT>{}, zonec, v[decltype(jc)::value], sl[decltype(jc)::value]);
+              finish_row(IntC<n>{}, IntC<EMIT>{}, zonec, v[decltype(jc)::value], sl[decltype(jc)::value], tap_e[decltype(jc)::value], tap_o[decltype(jc)::value]);
             }
           });
         });

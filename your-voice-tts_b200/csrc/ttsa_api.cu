@@ -439,16 +439,25 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   {
     const int np = c.win_length / 2 + (c.hop_length & 1), rh = (np + 31) / 32 * 32;
     const int emit_rows = ((c.hop_length + 1) / 2 + 31) / 32, npwx = (64 * emit_rows + 4 + 3) / 4 * 4;
-    h_wps.assign(2048 + 1024 + 2 * (size_t)rh + 4 + npwx, 0.f);
+    // window taps per LANE (kWpsWinStride consecutive floats: pair q = lane + 32 n at [lane][n], so a lane fetches its taps
+    // with 16-byte loads): wA[lane][n] = w[2q]; wB[r][n] = w[2 (r - 1 + 32 n) + 1], rows r = 0..32, i.e. row lane + 1 holds
+    // the odd taps of pair q and row lane those of pair q - 1 (frames that start one sample early); w = 0 outside the window
+    (void)rh;
+    h_wps.assign(2048 + 1024 + 65 * (size_t)kWpsWinStride + npwx, 0.f);
     float* q = h_wps.data();
     for (int i = 0; i < 2048; ++i) q[i] = h_tw[i];
     q += 2048;
     for (int i = 0; i < 1024; ++i) q[i] = h_g[i];
     q += 1024;
-    for (int i = 0; i < rh && i < 1024; ++i) q[i] = h_wE[i];
-    q += rh;
-    for (int i = 1; i < rh + 4 && i - 1 < 1024; ++i) q[i] = h_wO[i - 1];          // entry 0 = 0: the tap before the window
-    q += rh + 4;
+    for (int lane = 0; lane < 32; ++lane)
+      for (int n = 0; n < kWpsWinStride; ++n) q[lane * kWpsWinStride + n] = lane + 32 * n < 1024 ? h_wE[lane + 32 * n] : 0.f;
+    q += 32 * kWpsWinStride;
+    for (int r = 0; r < 33; ++r)
+      for (int n = 0; n < kWpsWinStride; ++n) {
+        const int pq = r - 1 + 32 * n;
+        q[r * kWpsWinStride + n] = (pq >= 0 && pq < 1024) ? h_wO[pq] : 0.f;
+      }
+    q += 33 * kWpsWinStride;
     for (int j = 0; j < npwx; ++j) q[j] = h_pw[(j - 1 + c.hop_length) % c.hop_length] * (1.0f / (float)kNfft);
   }
   // shared-memory image of the frame kernels' constant tables (Layout: [sm_wE, sm_mbar))
