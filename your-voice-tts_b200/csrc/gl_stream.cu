@@ -4,7 +4,7 @@
 
 namespace ttsa {
 
-template <int SRC, bool SC, int HOP, int WIN>
+template <int SRC, bool SC, int HOP, int WIN, bool FUSE>
 static const char* launch_one(int grid, cudaStream_t st, const Geo& g, const Tables& tb, const BatchDev& bd, const WpsDev& wp,
                               const FrameArgs& a) {
   cudaLaunchConfig_t cfg = {};
@@ -17,7 +17,7 @@ static const char* launch_one(int grid, cudaStream_t st, const Geo& g, const Tab
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gl_stream_kernel<SRC, SC, HOP, WIN>, g, tb, bd, wp, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gl_stream_kernel<SRC, SC, HOP, WIN, FUSE>, g, tb, bd, wp, a);
   g_launches += 1;
   if (e == cudaSuccess) e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
@@ -27,21 +27,34 @@ template <int HOP, int WIN>
 static const char* configure_geo() {
   if constexpr (!WpsGeo<HOP, WIN>::kFits) return nullptr;
   const char* e;
-  if ((e = set_smem(gl_stream_kernel<SRC_MAG, false, HOP, WIN>, 0))) return e;
-  if ((e = set_smem(gl_stream_kernel<SRC_MAG, true, HOP, WIN>, 0))) return e;
-  if ((e = set_smem(gl_stream_kernel<SRC_NORM_DB, false, HOP, WIN>, 0))) return e;
-  return set_smem(gl_stream_kernel<SRC_NORM_DB, true, HOP, WIN>, 0);
+  if ((e = set_smem(gl_stream_kernel<SRC_MAG, false, HOP, WIN, false>, 0))) return e;
+  if ((e = set_smem(gl_stream_kernel<SRC_MAG, true, HOP, WIN, false>, 0))) return e;
+  if ((e = set_smem(gl_stream_kernel<SRC_NORM_DB, false, HOP, WIN, false>, 0))) return e;
+  if ((e = set_smem(gl_stream_kernel<SRC_NORM_DB, true, HOP, WIN, false>, 0))) return e;
+  if ((e = set_smem(gl_stream_kernel<SRC_MAG, false, HOP, WIN, true>, 0))) return e;
+  if ((e = set_smem(gl_stream_kernel<SRC_MAG, true, HOP, WIN, true>, 0))) return e;
+  if ((e = set_smem(gl_stream_kernel<SRC_NORM_DB, false, HOP, WIN, true>, 0))) return e;
+  return set_smem(gl_stream_kernel<SRC_NORM_DB, true, HOP, WIN, true>, 0);
+}
+
+// several iterations per launch (FrameArgs::wps_iters > 1) run the FUSE instantiation; the one-iteration kernel has the
+// iteration loop compiled out
+template <int HOP, int WIN, bool FUSE>
+static const char* launch_geo_f(int src, bool sc, int grid, cudaStream_t st, const Geo& g, const Tables& tb, const BatchDev& bd,
+                                const WpsDev& wp, const FrameArgs& a) {
+  if constexpr (!WpsGeo<HOP, WIN>::kFits) return "gl_stream: geometry does not fit shared memory";
+  else
+  if (src == SRC_MAG) return sc ? launch_one<SRC_MAG, true, HOP, WIN, FUSE>(grid, st, g, tb, bd, wp, a)
+                                : launch_one<SRC_MAG, false, HOP, WIN, FUSE>(grid, st, g, tb, bd, wp, a);
+  return sc ? launch_one<SRC_NORM_DB, true, HOP, WIN, FUSE>(grid, st, g, tb, bd, wp, a)
+            : launch_one<SRC_NORM_DB, false, HOP, WIN, FUSE>(grid, st, g, tb, bd, wp, a);
 }
 
 template <int HOP, int WIN>
 static const char* launch_geo(int src, bool sc, int grid, cudaStream_t st, const Geo& g, const Tables& tb, const BatchDev& bd,
                               const WpsDev& wp, const FrameArgs& a) {
-  if constexpr (!WpsGeo<HOP, WIN>::kFits) return "gl_stream: geometry does not fit shared memory";
-  else
-  if (src == SRC_MAG) return sc ? launch_one<SRC_MAG, true, HOP, WIN>(grid, st, g, tb, bd, wp, a)
-                                : launch_one<SRC_MAG, false, HOP, WIN>(grid, st, g, tb, bd, wp, a);
-  return sc ? launch_one<SRC_NORM_DB, true, HOP, WIN>(grid, st, g, tb, bd, wp, a)
-            : launch_one<SRC_NORM_DB, false, HOP, WIN>(grid, st, g, tb, bd, wp, a);
+  return a.wps_iters > 1 ? launch_geo_f<HOP, WIN, true>(src, sc, grid, st, g, tb, bd, wp, a)
+                         : launch_geo_f<HOP, WIN, false>(src, sc, grid, st, g, tb, bd, wp, a);
 }
 
 bool gl_stream_supported(int hop, int win) {

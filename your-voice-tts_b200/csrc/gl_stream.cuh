@@ -53,6 +53,12 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 #ifndef TTSA_PROBE
 #define TTSA_PROBE 0
 #endif
+#ifndef TTSA_RING_GROUP
+#define TTSA_RING_GROUP 8
+#endif
+#ifndef TTSA_ZONE_DEFER
+#define TTSA_ZONE_DEFER 1
+#endif
 constexpr int kProbe = TTSA_PROBE;
 
 // One row of the spectrogram / one input span into the warp's buffer by ONE bulk asynchronous copy (the enclosing
@@ -171,7 +177,7 @@ struct WpsGeo {
 #define WPS_STAMP(k) do {} while (0)
 #endif
 
-template <int SRC, bool SC, int HOP, int WIN>
+template <int SRC, bool SC, int HOP, int WIN, bool FUSE>
 __global__ void __launch_bounds__(kWpsThreads, 1)
 gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev wp, const FrameArgs a) {
   using G = WpsGeo<HOP, WIN>;
@@ -250,7 +256,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
   // every other warp starts at once.  The same wait orders the write-after-read on the ping-pong buffers (the previous
   // warp's last frames read into this warp's region).  SMs therefore drift apart by whole frames between iterations: a
   // 14-frame run no longer makes 2 367 other warps wait at a kernel boundary, and launch / prologue / drain are paid once.
-  const int n_it = a.wps_iters;
+  const int n_it = FUSE ? a.wps_iters : 1;                        // (the loop costs the one-iteration kernel 2.7 % when it is not compiled out)
 #pragma unroll 1
   for (int it = 0; it < n_it; ++it) {
   const int epoch = a.wps_epoch + it;
@@ -286,7 +292,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
     // a run that starts inside the utterance leaves its first kZone samples as raw partial sums; the owner of the
     // frames before the cut finishes them at the end of its run
     const int zone_end = t_begin > 0 ? (t_begin - 1) * HOP + WIN / 2 : -(1 << 30);
-    bool zone_pending = zone_end > 0;
+    int zone_state = zone_end > 0 ? 1 : 0;                         // 1: head zone not stored yet, 2: stored, flag not published
     float sc_num = 0.0f, sc_den = 0.0f;
 
     // input span of frame t: samples [a0, a0 + WIN + p) of the utterance, a0 even; asynchronous when it needs no reflection
@@ -311,11 +317,10 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       }
       __syncwarp();
     };
-    bool x_bulk = false;
     auto span_issue = [&](int t) {                                 // returns the landing offset (0 or 2)
       const int s0 = t * HOP - WIN / 2;
       const int a0 = s0 - (s0 & 1);
-      if (span_fast(t)) { x_bulk = true; return span_to_smem_bulk_inside<WIN + 2>(buf, src + a0, lane, mbar_x); }
+      if (span_fast(t)) return span_to_smem_bulk_inside<WIN + 2>(buf, src + a0, lane, mbar_x);
       if (edge_async) {
         // the first and last frames of an utterance (np.pad(..., mode='reflect')): the part of the span that exists, from 8
         // samples before the frame (a reflected tap of the last frame can point just below it), by one bulk copy; the
@@ -329,10 +334,8 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(d), "l"(src + c_lo), "r"(bytes), "r"(mbar_x) : "memory");
         }
-        x_bulk = true;
         return a0 - A;
       }
-      x_bulk = false;
       // short utterances (several folds of the reflection inside one span).  Loads at gpu scope: with
       // several iterations per launch the same address is re-read after other SMs rewrote it, so no L1-allocating copy
 #pragma unroll 1
@@ -367,7 +370,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
         if (half == 0) {
           // ---------------------------------------------------------------- input span -> windowed packed frame
           if (kProbe & 2048) {
-          } else if (x_bulk) { mbar_wait(mbar_x, ph_x); ph_x ^= 1u; x_bulk = false; }
+          } else if (edge_async || span_fast(t)) { mbar_wait(mbar_x, ph_x); ph_x ^= 1u; }   // the span came by a bulk copy
           else cp_async_wait_all();
           __syncwarp();
           if (edge_async && !span_fast(t)) fill_reflected(a0, x_off);
@@ -568,7 +571,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       // array cannot be reordered by the compiler; a load-modify-store chain per row would expose the latency 18 times)
       auto pass_rows = [&](auto zonec, auto edgec) {
         constexpr bool ZONE = decltype(zonec)::value, EDGE = decltype(edgec)::value;
-        constexpr int kGroup = 8;                                  // two 16-byte loads of window taps per table and group
+        constexpr int kGroup = TTSA_RING_GROUP;                    // rows per group (a multiple of 4): 16-byte loads of the window taps
         static_for<0, (G::kRows + kGroup - 1) / kGroup>([&](auto gc) {
           constexpr int n0 = decltype(gc)::value * kGroup;
           float2 v[kGroup];
@@ -602,6 +605,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
           });
         });
       };
+      if (TTSA_ZONE_DEFER && zone_state == 2) { publish_flag(a.wps_flags + wi, epoch, l0); zone_state = 0; }
       if (kProbe & 16) {
       } else if (!edge) {
         if (a0 >= zone_end && newq > 0) pass_rows(IntC<0>{}, IntC<0>{});   // steady state
@@ -626,11 +630,15 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
       __syncwarp();
       newq = G::kNP - count;
       base += count; base = base >= G::kRH ? base - G::kRH : base;
-      if (zone_pending && a0 + 2 * count >= zone_end) {            // the head zone is stored: the owner of the frames before
-        publish_flag(a.wps_flags + wi, epoch, l0);                 // the cut may finish it (release at gpu scope)
-        zone_pending = false;
+      // the head zone is stored: the owner of the frames before the cut may finish it.  The flag is published one frame later
+      // (before that frame's stores): the fence of the release then finds this frame's stores long complete instead of
+      // waiting for them (2.6 % of all warp time sat in that fence)
+      if (zone_state == 1 && a0 + 2 * count >= zone_end) {
+        zone_state = 2;
+        if (!TTSA_ZONE_DEFER) { publish_flag(a.wps_flags + wi, epoch, l0); zone_state = 0; }
       }
     }  // frames of the run
+    if (zone_state == 2) { publish_flag(a.wps_flags + wi, epoch, l0); zone_state = 0; }
     WPS_STAMP(2);
 
     if constexpr (SC) {
