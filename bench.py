@@ -11,7 +11,10 @@ mel basis -> 60 Griffin-Lim iterations -> de-emphasis -- over 64 synthetic 6 s u
   e2e     same metric through the public AudioProcessor call with HOST buffers: pinned host mel -> device,
           compute, device -> pinned host waveform, all inside the timed region
   roofline  Griffin-Lim iteration kernel: algorithmic bytes per launch / measured launch duration vs the measured
-          HBM copy bandwidth (MEASURED_PEAKS.json); roofline_fp32: the FP32 pipe, the roof that actually binds
+          HBM copy bandwidth (MEASURED_PEAKS.json); one launch = one iteration over the batch (with TTSA_GL_FUSE=n a
+          launch runs n iterations and the figure is per iteration); roofline_fp32: the FP32 pipe, one of the three
+          resources that bind
+  gpu_launches  kernel launches of the library inside the timed region, counted by the library (ttsa_launch_count)
   e2e_dropin  the same 64 utterances through the reference-signature call, one ap.inv_mel_spectrogram(np.ndarray)
           per utterance, host arrays in and out, host-drawn random phases as the reference
   latency_single_ms  BASELINE configs[0]: one 6 s linear spectrogram through inv_spectrogram, device resident
