@@ -617,6 +617,48 @@ def test_feature_extraction_training_batch_cfg3():
         assert np.mean(np.abs(m - mo) <= FWD_TOL) >= 0.995 and np.all(np.abs(m - mo) <= _db_tol(ap, Dm.T, Dm.max(axis=1)).T)
 
 
+@pytest.mark.parametrize("sr,pre", [(22050, 0.98), (22050, 0.0), (16000, 0.97)])
+def test_feature_stream_kernel_ragged_vs_oracle_and_tile(monkeypatch, sr, pre):
+    """The warp-stream feature kernel (feat_stream.cuh) forced onto a small ragged batch (TTSA_FEAT_MINFRAMES=0) with a
+    2-CTA partition, so that runs cross utterance boundaries: utterances shorter than two spans (index-mapped path with
+    several folds of the reflection), first / last frames of long ones (bulk copy + mirrored fill), interior frames; with
+    and without pre-emphasis; odd (275) and even (200) hop; linear only, mel only and both.  Against the oracle per
+    utterance and against the tile kernel."""
+    from your_voice_tts_b200 import audio as A
+    audio = dict(MAIN_AUDIO, sample_rate=sr, preemphasis=pre)
+    orc = OracleAudioProcessor(**audio)
+    lens = [9000, 1, 551, 2300, 40000, 275, 1103, 6000, 2209]
+    wavs = [synth_speech_like(300 + i, n_samples=n) for i, n in enumerate(lens)]
+    res = {}
+    for kernel in ("stream", "tile"):
+        monkeypatch.setenv("TTSA_FEAT_KERNEL", kernel)
+        monkeypatch.setenv("TTSA_FEAT_MINFRAMES", "0")
+        monkeypatch.setenv("TTSA_WPS_GRID", "2")
+        A._PLAN_CACHE.clear()
+        ap = _ap(audio)
+        buf, lay = _packed_wavs(ap, wavs)
+        lin, mel = ap.features_batch(buf, lay)
+        lin_only, _ = ap.features_batch(buf, lay, want_mel=False)
+        _, mel_only = ap.features_batch(buf, lay, want_linear=False)
+        assert torch.equal(lin, lin_only) and torch.equal(mel, mel_only)
+        res[kernel] = ([x.cpu().numpy().copy() for x in lay.split_frames(lin)], [x.cpu().numpy().copy() for x in lay.split_frames(mel)])
+    for k in ("TTSA_FEAT_KERNEL", "TTSA_FEAT_MINFRAMES", "TTSA_WPS_GRID"):
+        monkeypatch.delenv(k)
+    A._PLAN_CACHE.clear()
+    ap = _ap(audio)
+    for u, w in enumerate(wavs):
+        lo, mo = orc.spectrogram(w).T, orc.melspectrogram(w).T
+        wp = orc.apply_preemphasis(w.astype(np.float32)) if pre != 0 else w.astype(np.float32)
+        D = np.abs(orc._stft(wp)).T
+        Dm = orc._linear_to_mel(D.T).T
+        l, m = res["stream"][0][u], res["stream"][1][u]
+        assert l.shape == lo.shape and m.shape == mo.shape, (u, l.shape, lo.shape)
+        assert np.mean(np.abs(l - lo) <= FWD_TOL) >= 0.99 and np.all(np.abs(l - lo) <= _db_tol(ap, D.T, D.max(axis=1)).T), (sr, pre, u)
+        assert np.mean(np.abs(m - mo) <= FWD_TOL) >= 0.99 and np.all(np.abs(m - mo) <= _db_tol(ap, Dm.T, Dm.max(axis=1)).T), (sr, pre, u)
+        lt, mt = res["tile"][0][u], res["tile"][1][u]
+        assert np.mean(np.abs(l - lt) <= FWD_TOL) >= 0.99 and np.mean(np.abs(m - mt) <= FWD_TOL) >= 0.99, (sr, pre, u)
+
+
 # ------------------------------------------------------------------------------------------------ post-processing
 def _packed_wavs(ap, wavs):
     lay = ap.layout(wav_lengths=[len(w) for w in wavs])
@@ -809,10 +851,19 @@ def test_full_size_properties_64x6s():
         b = lay_f.split_wav(yg)[u].cpu().numpy()
         assert snr_db(a, b) >= 80.0, snr_db(a, b)
     # batched features == single-utterance features
+    # (the batch runs the warp-stream feature kernel, the single call the tile kernel: both within the forward bar of the
+    # oracle, and of each other within twice the float32 conditioning of log|X|)
     lin, mel = ap.features_batch(wav, lay)
     one = wav[int(lay.wav_off[5]):int(lay.wav_off[5]) + Lw].cpu().numpy()
-    np.testing.assert_allclose(lin[5 * 482:6 * 482].cpu().numpy().T, ap.spectrogram(one), atol=1e-6)
-    np.testing.assert_allclose(mel[5 * 482:6 * 482].cpu().numpy().T, ap.melspectrogram(one), atol=1e-6)
+    orc = OracleAudioProcessor(**dict(MAIN_AUDIO, griffin_lim_iters=3))
+    Do = np.abs(orc._stft(orc.apply_preemphasis(one.astype(np.float32))))          # [1025, 482]
+    Dmo = orc._linear_to_mel(Do)
+    for got_b, got_1, ref, amp in ((lin[5 * 482:6 * 482].cpu().numpy().T, ap.spectrogram(one), orc.spectrogram(one), Do),
+                                   (mel[5 * 482:6 * 482].cpu().numpy().T, ap.melspectrogram(one), orc.melspectrogram(one), Dmo)):
+        tol = _db_tol(ap, amp, amp.max(axis=0))
+        assert np.mean(np.abs(got_b - ref) <= FWD_TOL) >= 0.995 and np.all(np.abs(got_b - ref) <= tol)
+        assert np.mean(np.abs(got_1 - ref) <= FWD_TOL) >= 0.995 and np.all(np.abs(got_1 - ref) <= tol)
+        assert np.all(np.abs(got_b - got_1) <= 2 * tol)
 
 
 def test_fast_griffin_lim_momentum_opt_in():

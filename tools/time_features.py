@@ -11,10 +11,19 @@ lin, mel = ap.features_batch(wav, lay)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 lin = torch.empty_like(lin); mel = torch.empty_like(mel)
+what = sys.argv[2] if len(sys.argv) > 2 else "both"          # both | lin | mel
+g = torch.cuda.CUDAGraph()                                    # graph replay: no host overhead between the launches
+def call():
+    ap.features_batch(wav, lay, want_linear=what != "mel", want_mel=what != "lin", lin_out=lin if what != "mel" else None,
+                      mel_out=mel if what != "lin" else None)
+call(); torch.cuda.synchronize()
+with torch.cuda.graph(g):
+    for _ in range(20):
+        call()
+g.replay(); torch.cuda.synchronize()
 a.record()
-for _ in range(20):
-    ap.features_batch(wav, lay, lin_out=lin, mel_out=mel)
+g.replay()
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 20
 bytes_ = B * (132300 * 4 + 482 * 1025 * 4 + 482 * 80 * 4)
-print("features B=%d: %.4f ms per batch, %.1f GB/s algorithmic (%.1f %% of 6550.7), %.0f audio-s/s" % (B, ms, bytes_ / ms / 1e6, 100 * bytes_ / ms / 1e6 / 6550.7, B * 6.0 / ms * 1e3))
+print("features[%s] B=%d: %.4f ms per batch, %.1f GB/s algorithmic (%.1f %% of 6550.7), %.0f audio-s/s" % (what, B, ms, bytes_ / ms / 1e6, 100 * bytes_ / ms / 1e6 / 6550.7, B * 6.0 / ms * 1e3))

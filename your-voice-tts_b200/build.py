@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 TAG = os.environ.get("TTSA_BUILD_TAG", "")                # experiments only: a second library next to the shipped one
 OBJ = os.path.join(HERE, "build" + TAG)
 LIB = os.path.join(HERE, "libttsa_b200%s.so" % TAG)
-SOURCES = ["ttsa_api.cu", "gl_stream.cu", "frame_gl.cu", "frame_gl_mom.cu", "frame_synth.cu", "frame_analysis.cu"]
+SOURCES = ["ttsa_api.cu", "gl_stream.cu", "feat_stream.cu", "frame_gl.cu", "frame_gl_mom.cu", "frame_synth.cu", "frame_analysis.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("TTSA_NVCC_EXTRA", "").split()      # experiments only (e.g. -DTTSA_WPS_WARPS=8)
 FLAGS = EXTRA + ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

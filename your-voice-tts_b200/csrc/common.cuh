@@ -66,6 +66,7 @@ struct Geo {
   int num_mels;
   int mel_smem_floats;       // > 0: the compact mel basis (Tables::mel_compact) fits behind Layout::sm_total in the
                              //      feature kernel's shared memory; 0: read the banded basis from global memory
+  int mel_steps;             // > 0: steps of the lane schedule (Tables::mel_sched) of the warp-stream feature kernel
   // spectrogram value -> magnitude:  S = exp2(c1 * clip(x, lo, hi) + c0)   (denormalize, +ref, db_to_amp, **power fused)
   float s_c1, s_c0, s_lo, s_hi;
   // amplitude -> normalised dB:      v = clip(n_a * log2(max(min_amp, a)) + n_b, n_lo, n_hi)
@@ -95,6 +96,8 @@ struct Tables {
   int mel_ld;
   // the same basis without padding: int2 (first tap index in mel_cval, first bin) per filter, one extra entry, then the taps
   const float* mel_compact;
+  // lane schedule of the same basis for feat_stream.cuh: float4 (w0, w1, w2, bin) [Geo::mel_steps][32], then int [3][32] filter ids
+  const float* mel_sched;
 };
 
 // Batch layout on the device.
@@ -105,6 +108,7 @@ struct BatchDev {
   const long long* wav_off;  // [B+1] (multiples of 4)
   const int* tile_off;       // [B+1] prefix sum of ceil(T/kNF)
   const int* fine_off;       // [B+1] prefix sum of the fine segments per utterance (frame_kernel<..., FINE>)
+  const int* tsum;           // [B+1] prefix sum of the frame counts (flattened frame index; feat_stream.cuh), or nullptr when it overflows int
   int B;
   int total_tiles;
   int total_fine;

@@ -163,7 +163,11 @@ __device__ __forceinline__ float spec_to_mag(float x, const Geo& g) {
 
 __device__ __forceinline__ float amp_to_norm_db(float a, const Geo& g) {
   // lg2.approx: absolute error ~1e-7 in log2, i.e. ~1e-6 dB -- two orders below the float32 conditioning of |X| itself
-  const float v = fmaf(g.n_a, __log2f(fmaxf(g.min_amp, a)), g.n_b);
+  // (.ftz: the argument is at least min_amp = 10^(min_level_db / 20), a normal number for any sensible config, so the three
+  // instructions with which __log2f rescales denormal arguments are dead weight -- 36 calls per frame in the feature kernels)
+  float lg;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(fmaxf(g.min_amp, a)));
+  const float v = fmaf(g.n_a, lg, g.n_b);
   return fminf(fmaxf(v, g.n_lo), g.n_hi);
 }
 
@@ -656,10 +660,16 @@ frame_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a)
               magbuf[992 - k0] = sqrt_fast(XpR.y * XpR.y + XpI.y * XpI.y);
             }
           });
-          if (l0) {   // k = 512: X = conj(Z[512])
-            const float2 Xc = make_float2(R[8].x, -I[8].x);
-            if constexpr (SRC == OUT_COMPLEX) cout[512] = cmul(Xc, shift_phasor(512, lpad, -1.0f));
-            else magbuf[512] = sqrt_fast(Xc.x * Xc.x + Xc.y * Xc.y);
+          if constexpr (SRC == OUT_COMPLEX) {
+            if (l0) {   // k = 512: X = conj(Z[512])
+              const float2 Xc = make_float2(R[8].x, -I[8].x);
+              cout[512] = cmul(Xc, shift_phasor(512, lpad, -1.0f));
+            }
+          } else {
+            // k = 512 is lane 0's: every lane stores lane 0's value.  A lane-dependent branch here is not reconverged before
+            // the contraction below, which then runs once for lane 0 and once for the other 31 (measured in feat_stream.cuh)
+            const float am = sqrt_fast(R[8].x * R[8].x + I[8].x * I[8].x);
+            magbuf[512] = __shfl_sync(0xffffffffu, am, 0);
           }
           if constexpr (SRC == OUT_FEATURES) {
             __syncwarp();

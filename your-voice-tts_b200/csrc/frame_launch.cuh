@@ -27,6 +27,12 @@ const char* configure_gl_stream();
 const char* launch_gl_stream(int src, bool sc, int hop, int win, int grid, cudaStream_t st, const Geo&, const Tables&, const BatchDev&,
                              const WpsDev&, const FrameArgs&);
 
+// warp-stream feature extraction kernel (feat_stream.cu)
+bool feat_stream_supported(int hop, int win, int mel_smem_floats);
+const char* configure_feat_stream();
+const char* launch_feat_stream(int hop, int win, int grid, cudaStream_t st, const Geo&, const Tables&, const BatchDev&, const FrameArgs&,
+                               int total_frames);
+
 template <class K>
 inline const char* set_smem(K kernel, size_t /*smem_bytes*/) {
   // The attribute belongs to the function, not to a plan: opt in to the device maximum (227 KB on sm_100) once, so that

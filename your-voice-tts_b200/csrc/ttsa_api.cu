@@ -1,4 +1,5 @@
 // C ABI of libttsa_b200.so (see include/ttsa.h).  Host logic: plan tables, batch layout, kernel orchestration.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -72,6 +73,7 @@ struct ttsa_plan {
   bool fine_ok = true;             // small batches may use the fine-segment form of the tile kernel (TTSA_GL_FINE=0: never)
   bool fixed_geo = true;           // use the kernels compiled for this (hop, win) when they exist (TTSA_GENERIC_GEO=1: never)
   int wps_grid = 0;                // CTAs of the warp-stream kernel (= SMs; TTSA_WPS_GRID overrides it for tests)
+  bool feat_stream = false;        // features run the warp-stream kernel (feat_stream.cuh) on batches with enough frames
   bool gl_stream = false;          // Griffin-Lim iterations run the warp-stream kernel (gl_stream.cuh) when the batch has a
                                    // partition for it; TTSA_GL_KERNEL=tile keeps the tile kernel (frame_kernels.cuh)
   // device allocations
@@ -98,6 +100,8 @@ struct ttsa_batch {
   bool wps_ok = false;
   int wps_grid = 0, wps_win = 0;
   std::vector<int> wps_cut, tsum, wps_u0;
+  std::vector<int> tsum_all;       // prefix sum of the frame counts (empty when it overflows int); feat_stream.cuh
+  int feat_frames = 0;             // sum of the frame counts (0: not available)
   WpsDev wps_dev{nullptr, nullptr, nullptr};
   void* d_block = nullptr;
   BatchDev dev;
@@ -507,6 +511,76 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     const bool fits = ((size_t)ly.sm_total + h_melc.size()) * 4 <= per_cta_limit;
     p->geo.mel_smem_floats = fits ? (int)h_melc.size() : 0;
   }
+  // Lane schedule of the banded basis for the warp-stream feature kernel (feat_stream.cuh): every lane owns up to three
+  // filters (longest-first onto the least loaded lane, so all lanes walk about sum(taps) / 32 taps instead of the three
+  // longest filters back to back) and walks its taps in an order chosen so that the 32 lanes of a step read 32 different
+  // shared-memory banks of the magnitude row.  Entry [step][lane] = (w0, w1, w2, bin): the tap's weight sits in the slot of
+  // the lane's filter it belongs to, the other two are zero, so a step is one 16-byte load, one magnitude load and three
+  // FMAs with no branch; then [3][32] filter indices (-1: none).
+  std::vector<float> h_msched;
+  p->geo.mel_steps = 0;
+  if (c.num_mels <= 96) {
+    struct Tap { int bin; float w; int slot; };
+    std::vector<std::vector<Tap>> lane_taps(32);
+    std::vector<int> lane_nf(32, 0), fid(96, -1);
+    std::vector<int> order(c.num_mels);
+    for (int m = 0; m < c.num_mels; ++m) order[m] = m;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return h_cnt[x] > h_cnt[y]; });
+    for (int m : order) {
+      int best = -1;
+      for (int l = 0; l < 32; ++l)
+        if (lane_nf[l] < 3 && (best < 0 || lane_taps[l].size() < lane_taps[best].size())) best = l;
+      const int slot = lane_nf[best]++;
+      fid[slot * 32 + best] = m;
+      for (int cidx = 0; cidx < h_cnt[m]; ++cidx) {
+        const float w = h_val[(size_t)m * ld + cidx];
+        if (w != 0.0f) lane_taps[best].push_back({h_lo[m] + cidx, w, slot});
+      }
+    }
+    size_t steps = 1;
+    for (int l = 0; l < 32; ++l) steps = std::max(steps, lane_taps[l].size());
+    h_msched.assign(steps * 32 * 4 + 96, 0.f);
+    std::vector<std::vector<char>> done(32);
+    for (int l = 0; l < 32; ++l) done[l].assign(lane_taps[l].size(), 0);
+    std::vector<size_t> left(32);
+    for (int l = 0; l < 32; ++l) left[l] = lane_taps[l].size();
+    for (size_t st = 0; st < steps; ++st) {
+      unsigned used = 0;                                            // banks read in this step
+      std::vector<int> lanes(32);
+      for (int l = 0; l < 32; ++l) lanes[l] = l;
+      // lanes that cannot afford an idle step choose first
+      std::stable_sort(lanes.begin(), lanes.end(), [&](int x, int y) { return left[x] > left[y]; });
+      for (int l : lanes) {
+        float* e = &h_msched[(st * 32 + l) * 4];
+        const bool must = left[l] >= steps - st;                    // no idle step left for this lane
+        int pick = -1;
+        for (size_t i = 0; i < lane_taps[l].size(); ++i)
+          if (!done[l][i] && !(used >> (lane_taps[l][i].bin & 31) & 1u)) { pick = (int)i; break; }
+        if (pick < 0 && must)
+          for (size_t i = 0; i < lane_taps[l].size(); ++i) if (!done[l][i]) { pick = (int)i; break; }   // a bank conflict
+        int bin = 0;
+        if (pick >= 0) {
+          const Tap& t = lane_taps[l][pick];
+          done[l][pick] = 1; --left[l];
+          e[t.slot] = t.w;
+          bin = t.bin;
+        } else {                                                    // idle step: zero weights, a bin in a free bank
+          for (int b = 0; b < 32; ++b) if (!(used >> b & 1u)) { bin = b; break; }
+        }
+        used |= 1u << (bin & 31);
+        std::memcpy(&e[3], &bin, 4);
+      }
+    }
+    bool all = true;
+    for (int l = 0; l < 32; ++l) all = all && left[l] == 0;
+    if (all) {
+      std::memcpy(&h_msched[steps * 32 * 4], fid.data(), 96 * 4);
+      p->geo.mel_steps = (int)steps;
+
+    } else {
+      h_msched.clear();
+    }
+  }
   p->pinv_chunks = (c.num_mels + kTcChunk - 1) / kTcChunk;
   const std::vector<uint16_t> h_pinv_tc = canon_split_b(p->h_inv_mel, kF, c.num_mels, 208, 5, p->pinv_chunks);
   std::vector<uint16_t> h_mel_tc;
@@ -523,7 +597,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       {h_pinv_tc.data(), h_pinv_tc.size() * 2, 0}, {h_mel_tc.data(), h_mel_tc.size() * 2, 0},
       {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}, {h_img.data(), h_img.size() * 4, 0},
       {h_melc.data(), h_melc.size() * 4, 0}, {h_pw2.data(), h_pw2.size() * 4, 0}, {h_wps.data(), h_wps.size() * 4, 0},
-      {h_edge_head.data(), h_edge_head.size() * 4, 0}, {h_edge_tail.data(), h_edge_tail.size() * 4, 0}};
+      {h_edge_head.data(), h_edge_head.size() * 4, 0}, {h_edge_tail.data(), h_edge_tail.size() * 4, 0},
+      {h_msched.data(), h_msched.size() * 4, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -549,6 +624,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->tb.pw = (const float*)(base + pieces[4].off);
   p->tb.pw2 = (const float2*)(base + pieces[16].off);
   p->tb.wps_image = (const float*)(base + pieces[17].off);
+  p->tb.mel_sched = h_msched.empty() ? nullptr : (const float*)(base + pieces[20].off);
   p->tb.edge_head = (const float*)(base + pieces[18].off);
   p->tb.edge_tail = (const float*)(base + pieces[19].off);
   p->tb.mel_lo = (const int*)(base + pieces[5].off);
@@ -570,6 +646,16 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
     p->wps_grid = (wg != nullptr && std::atoi(wg) > 0) ? std::min(std::atoi(wg), p->num_sms) : p->num_sms;
     if (p->gl_stream) {
       err = configure_gl_stream();
+      if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
+    }
+  }
+  if (feat_stream_supported(c.hop_length, c.win_length, p->geo.mel_steps > 0 ? p->geo.mel_steps * 128 + 96 : p->geo.mel_smem_floats)) {
+    const char* fk = std::getenv("TTSA_FEAT_KERNEL");
+    p->feat_stream = !(fk != nullptr && std::strcmp(fk, "tile") == 0);
+    const char* wg = std::getenv("TTSA_WPS_GRID");
+    p->wps_grid = (wg != nullptr && std::atoi(wg) > 0) ? std::min(std::atoi(wg), p->num_sms) : p->num_sms;
+    if (p->feat_stream) {
+      err = configure_feat_stream();
       if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
     }
   }
@@ -753,8 +839,18 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
   }
   if (plan->device >= 0) {
     DeviceGuard guard(plan->device);
+    {
+      long long acc = 0;
+      b->tsum_all.assign(B + 1, 0);
+      for (int u = 0; u < B && acc >= 0; ++u) {
+        acc += b->T[u];
+        if (acc > 0x3fffffff) acc = -1; else b->tsum_all[u + 1] = (int)acc;
+      }
+      if (acc < 0) b->tsum_all.clear();
+      b->feat_frames = acc > 0 ? (int)acc : 0;
+    }
     const size_t n_wps = b->wps_ok ? b->tsum.size() + b->wps_cut.size() + b->wps_u0.size() : 0;
-    const size_t n_i = (size_t)B * 2 + (size_t)(B + 1) * 3 + n_wps;     // T, wav_len, tile_off, chunk_off, [tsum, wps_cut, wps_u0], fine_off
+    const size_t n_i = (size_t)B * 2 + (size_t)(B + 1) * 3 + n_wps + b->tsum_all.size();   // T, wav_len, tile_off, chunk_off, [tsum, wps_cut, wps_u0], fine_off, [tsum_all]
     const size_t bytes_i = (n_i * 4 + 15) / 16 * 16;
     const size_t bytes_l = (size_t)(B + 1) * 2 * 8;
     if (cudaMalloc(&b->d_block, bytes_i + bytes_l) != cudaSuccess) { delete b; return fail(TTSA_ERR_CUDA, "cudaMalloc for batch layout failed"); }
@@ -774,6 +870,7 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
     }
     const size_t fine_at = 2 * (size_t)B + 2 * (size_t)(B + 1) + n_wps;
     std::memcpy(hi + fine_at, b->fine_off.data(), (B + 1) * 4);
+    if (!b->tsum_all.empty()) std::memcpy(hi + fine_at + (B + 1), b->tsum_all.data(), (B + 1) * 4);
     cudaError_t e = cudaMemcpy(b->d_block, h.data(), h.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(b->d_block); delete b; return fail(TTSA_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e)); }
     const long long* dl = (const long long*)b->d_block;
@@ -784,6 +881,7 @@ static int batch_finish(const ttsa_plan* plan, ttsa_batch* b, ttsa_batch** out, 
     b->dev.wav_len = di + B;
     b->dev.tile_off = di + 2 * B;
     b->dev.fine_off = di + fine_at;
+    b->dev.tsum = b->tsum_all.empty() ? nullptr : di + fine_at + (B + 1);
     b->d_chunk_off = di + 2 * B + (B + 1);
     if (b->wps_ok) {
       b->wps_dev.tsum = di + 2 * B + 2 * (B + 1);
@@ -891,6 +989,18 @@ extern "C" int ttsa_stft_features(const ttsa_plan* plan, const ttsa_batch* batch
   a.wav_in = wav_dev; a.lin_out = lin_out_dev; a.mel_out = mel_out_dev;
   a.preemph = (flags & TTSA_FEAT_PREEMPHASIS) ? 1 : 0;
   if (plan->generic) return gen_launch(plan, batch, MODE_ANALYSIS, OUT_FEATURES, a, (cudaStream_t)stream);
+  // warp-stream kernel from two frames per warp of the GPU upwards (TTSA_FEAT_MINFRAMES overrides the threshold,
+  // TTSA_FEAT_KERNEL=tile the choice); the tile kernel serves smaller batches and run-time geometries
+  if (plan->feat_stream && plan->fixed_geo && batch->dev.tsum != nullptr) {
+    int min_frames = 2;
+    if (const char* mf = std::getenv("TTSA_FEAT_MINFRAMES")) min_frames = std::max(0, std::atoi(mf));
+    if ((long long)batch->feat_frames >= (long long)min_frames * plan->wps_grid * kWpsWarps && batch->feat_frames > 0) {
+      const char* err = launch_feat_stream(plan->cfg.hop_length, plan->cfg.win_length, plan->wps_grid, (cudaStream_t)stream, plan->geo,
+                                           plan->tb, batch->dev, a, batch->feat_frames);
+      if (err) return fail(TTSA_ERR_CUDA, "feature stream kernel launch: %s", err);
+      return TTSA_OK;
+    }
+  }
   return launch_frames(plan, batch, MODE_ANALYSIS, OUT_FEATURES, false, a, (cudaStream_t)stream);
 }
 
