@@ -11,7 +11,9 @@ static const char* launch_one(int grid, cudaStream_t st, const Geo& g, const Tab
   else {
     const size_t mel_floats = g.mel_steps > 0 ? (size_t)g.mel_steps * 128 + 96 : (size_t)g.mel_smem_floats;
     const size_t smem = ((size_t)FeatGeo<HOP, WIN>::sm_mel + (a.mel_out != nullptr ? mel_floats : 0)) * 4;
-    feat_stream_kernel<HOP, WIN><<<grid, kWpsThreads, smem, st>>>(g, tb, bd, a, total_frames);
+    if (a.lin_out != nullptr && a.mel_out != nullptr) feat_stream_kernel<HOP, WIN, true, true><<<grid, kWpsThreads, smem, st>>>(g, tb, bd, a, total_frames);
+    else if (a.lin_out != nullptr) feat_stream_kernel<HOP, WIN, true, false><<<grid, kWpsThreads, smem, st>>>(g, tb, bd, a, total_frames);
+    else feat_stream_kernel<HOP, WIN, false, true><<<grid, kWpsThreads, smem, st>>>(g, tb, bd, a, total_frames);
     g_launches += 1;
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
@@ -27,7 +29,10 @@ bool feat_stream_supported(int hop, int win, int mel_smem_floats) {
 
 const char* configure_feat_stream() {
   const char* e;
-#define TTSA_X(H, W) if constexpr (FeatGeo<H, W>::kFits) { if ((e = set_smem(feat_stream_kernel<H, W>, 0))) return e; }
+#define TTSA_X(H, W) if constexpr (FeatGeo<H, W>::kFits) { \
+    if ((e = set_smem(feat_stream_kernel<H, W, true, true>, 0))) return e; \
+    if ((e = set_smem(feat_stream_kernel<H, W, true, false>, 0))) return e; \
+    if ((e = set_smem(feat_stream_kernel<H, W, false, true>, 0))) return e; }
   TTSA_FIXED_GEOS(TTSA_X)
 #undef TTSA_X
   return nullptr;

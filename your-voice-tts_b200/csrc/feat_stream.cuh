@@ -37,7 +37,9 @@ struct FeatGeo {
   static constexpr bool kFits = kFeatSpanAt + 12 + kSpan + 3 <= kBufFloats && (sm_mel + 2048) * 4 <= 227 * 1024;
 };
 
-template <int HOP, int WIN>
+// LIN / MEL: which outputs the launch produces (compile-time, so that the output stage has no branch the compiler must
+// treat as possibly divergent around the warp shuffles)
+template <int HOP, int WIN, bool LIN, bool MEL>
 __global__ void __launch_bounds__(kWpsThreads, 1)
 feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameArgs a, const int total_frames) {
   using G = WpsGeo<HOP, WIN>;
@@ -62,7 +64,7 @@ feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameA
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(tb.wps_image), "r"(bytes), "r"(mbar) : "memory");
   }
-  if (a.mel_out != nullptr) {
+  if (MEL) {
     if (g.mel_steps > 0) for (int i = tid; i < g.mel_steps * 128 + 96; i += kWpsThreads) smem[FG::sm_mel + i] = tb.mel_sched[i];
     else for (int i = tid; i < g.mel_smem_floats; i += kWpsThreads) smem[FG::sm_mel + i] = tb.mel_compact[i];
   }
@@ -237,8 +239,8 @@ feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameA
       // ---------------------------------------------------------------------- spectrum -> |X| -> outputs
       // X[k] = (E2 + G_k D2) / 2, X[1024 - k] = conj(E2 - G_k D2) / 2 on conjugate pairs (k, 1024 - k) of the packed transform
       const long long row = row0 + t;
-      float* const lout = a.lin_out != nullptr ? a.lin_out + row * kF : nullptr;
-      const bool want_mel = a.mel_out != nullptr;
+      float* const lout = LIN ? a.lin_out + row * kF : nullptr;
+      constexpr bool want_mel = MEL;
       float* const magbuf = buf;
       static_for<0, 8>([&](auto mc) {
         constexpr int m = decltype(mc)::value;
@@ -262,7 +264,7 @@ feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameA
         const float2 mk = __fmul2_rn(__ffma2_rn(XkI, XkI, __fmul2_rn(XkR, XkR)), splat(0.25f));
         const float2 mp = __fmul2_rn(__ffma2_rn(XpI, XpI, __fmul2_rn(XpR, XpR)), splat(0.25f));
         const float a0m = sqrt_fast(mk.x), a1m = sqrt_fast(mk.y), a2m = sqrt_fast(mp.x), a3m = sqrt_fast(mp.y);
-        if (lout != nullptr) {
+        if (LIN) {
           lout[k0] = amp_to_norm_db(a0m, g);
           lout[k0 + 32] = amp_to_norm_db(a1m, g);
           lout[1024 - k0] = amp_to_norm_db(a2m, g);
@@ -276,7 +278,7 @@ feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameA
           // reconverged before the end of the frame and the mel contraction below would run once per half of the warp
         const float am = sqrt_fast(R[8].x * R[8].x + I[8].x * I[8].x);
         const float dbv = amp_to_norm_db(am, g);
-        if (l0 && lout != nullptr) lout[512] = dbv;
+        if (LIN && l0) lout[512] = dbv;
         const float am0 = __shfl_sync(0xffffffffu, am, 0);
         if (want_mel) magbuf[512] = am0;                          // every lane, same value: no lane-dependent branch
       }
@@ -288,7 +290,7 @@ feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameA
           // magnitude reads of a step in 32 different banks; one 16-byte load, one magnitude load, three FMAs per step
           const float4* const sch = reinterpret_cast<const float4*>(smem + FG::sm_mel) + lane;
           float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
           for (int st = 0; st < g.mel_steps; ++st) {
             const float4 e = sch[32 * st];
             const float mg = magbuf[__float_as_int(e.w)];
