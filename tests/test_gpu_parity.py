@@ -945,8 +945,9 @@ def test_tacotron2_output_to_waveform_cfg4(tacotron2_postnet):
 
 
 def test_mel_gemm_variants_agree(monkeypatch):
-    """mel <-> linear: the pipelined tcgen05 kernel (default), the un-pipelined tensor-core kernel (TTSA_MEL_GEMM=tc_simple)
-    and the fp32 SIMT kernels (TTSA_MEL_GEMM=simt) all meet the float64 product within the same bound."""
+    """mel <-> linear: the transposed warp-specialised tcgen05 kernel (default), the round-1 pipelined kernel
+    (TTSA_MEL_GEMM=tc96), the un-pipelined tensor-core kernel (tc_simple) and the fp32 SIMT kernels (simt) all meet the
+    float64 product within the same bound; T = 300 frames is three frame tiles with a ragged last one."""
     from your_voice_tts_b200 import audio as A
     orc = OracleAudioProcessor(**MAIN_AUDIO)
     rng = np.random.default_rng(12)
@@ -955,7 +956,7 @@ def test_mel_gemm_variants_agree(monkeypatch):
     lin_amp = (rng.random((1025, T)) ** 3).astype(np.float32) * 5.0
     want_lin = np.maximum(1e-10, np.linalg.pinv(orc._build_mel_basis()) @ mel_amp.astype(np.float64))
     want_mel = orc._build_mel_basis() @ lin_amp.astype(np.float64)
-    for mode in ("", "tc_simple", "simt"):
+    for mode in ("", "tc96", "tc_simple", "simt"):
         if mode:
             monkeypatch.setenv("TTSA_MEL_GEMM", mode)
         A._PLAN_CACHE.clear()

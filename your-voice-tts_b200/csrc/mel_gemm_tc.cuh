@@ -414,3 +414,211 @@ __global__ void __launch_bounds__(kM2lThreads, 1) mel_to_linear_tc_kernel(const 
 }
 
 }  // namespace ttsa
+
+// ---------------------------------------------------------------------------------------------------------
+// mel -> linear, transposed and warp-specialised (num_mels <= 80): D^T[bins x frames] = pinv[bins x K] * amp[frames x K]^T.
+//   With the BINS as the UMMA M dimension a TMEM lane is a bin and a column a frame, so after tcgen05.ld (one lane per
+//   thread) the 32 lanes of a warp hold 32 consecutive bins of one frame in each register: every register goes to HBM
+//   with one coalesced 128-byte store, straight from registers -- no shared-memory staging and no CTA barrier in the
+//   epilogue (the kernel above spends 3.4 us per 128 x 96 tile there, where the 30 MMAs need 0.7 us).
+//   16 epilogue warps (TMEM lane group = warp % 4, 32 frames each = warp / 4) + 1 producer warp whose lane 0 streams the
+//   pre-split pseudo-inverse tiles (one 60 KB bulk copy per 128-bin tile, two buffers) and issues the MMAs into two
+//   alternating TMEM accumulators.  mbarriers: tile landed (tx bytes), accumulator full (tcgen05.commit), accumulator
+//   drained (one arrival per epilogue warp, right after its tcgen05.ld).  The frame operand (128 frames x 80 mels, three
+//   bf16 terms) is converted once per frame tile by the epilogue warps.
+// ---------------------------------------------------------------------------------------------------------
+namespace ttsa {
+
+constexpr int kT2Bins = 128;                       // UMMA M: bins per tile
+constexpr int kT2Tiles = 9;                        // 1152 >= 1025 bins
+constexpr int kT2Frames = 128;                     // UMMA N: frames per tile
+constexpr int kT2EpiWarps = 16;
+constexpr int kT2Threads = (kT2EpiWarps + 1) * 32; // + the producer warp
+constexpr uint32_t kT2PartBytes = 128 * kTcChunk * 2;            // one bf16 term of a 128-row operand: 20 480
+constexpr uint32_t kT2TileBytes = 3 * kT2PartBytes;              // 61 440
+constexpr size_t kT2Smem = (size_t)kT2TileBytes * 3 + 1024;      // frames + two pinv buffers (+ alignment slack)
+#ifndef TTSA_T2_PIECES
+#define TTSA_T2_PIECES 12
+#endif
+constexpr int kT2Pieces = TTSA_T2_PIECES;                        // bulk copies per pseudo-inverse tile (5 KB each)
+static_assert(kT2TileBytes % (16 * kT2Pieces) == 0, "pieces of whole 16-byte units");
+
+template <int X>
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+      "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kT2Threads, 1) mel_to_linear_tc2_kernel(const TcGemmParams p, const int n_ftiles) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  constexpr uint32_t kLbo = (128 / 8) * 128;       // byte stride between 8-element K blocks of a 128-row operand
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kT2Frames >> 3) << 17) | ((uint32_t)(kT2Bins >> 4) << 24);
+  unsigned char* const smF = tc_smem;                            // frames: 3 parts
+  unsigned char* const smP = tc_smem + kT2TileBytes;             // pseudo-inverse tiles: 2 buffers of 3 parts
+  __shared__ __align__(8) uint64_t mbar[6];                      // 0,1 tile landed; 2,3 accumulator full; 4,5 accumulator drained
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&mbar[0]);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i) : "memory");
+    for (int i = 4; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * i), "r"(kT2EpiWarps) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t smF_addr = (uint32_t)__cvta_generic_to_shared(smF);
+  const uint32_t smP_addr = (uint32_t)__cvta_generic_to_shared(smP);
+  const bool pow15 = p.mp.power == 1.5f;
+  const bool producer = warp == kT2EpiWarps;
+  uint32_t n_tile = 0;                             // (frame tile, bin tile) pairs this CTA has started: buffer = n_tile & 1, use = n_tile >> 1
+
+  for (int ft = blockIdx.x; ft < n_ftiles; ft += gridDim.x) {
+    const long long row0 = (long long)ft * kT2Frames;
+    if (!producer) {
+      // ---- frames: fp32 mel -> amplitude -> three bf16 terms, canonical K-major layout; thread (row, quarter) converts
+      //      3 / 3 / 2 / 2 K blocks of 8.  Every MMA of the previous frame tile is complete: the epilogue warps have waited
+      //      for its last accumulator.
+      const int r = tid >> 2, quarter = tid & 3;
+      const long long row = row0 + r;
+      const int kb0 = quarter < 2 ? 3 * quarter : 6 + 2 * (quarter - 2), nkb = quarter < 2 ? 3 : 2;
+      // all of the thread's 24 (16) values are requested before the first is used: one exposed load latency per frame tile
+      float xin[24];
+      const float* const arow = p.a + row * p.lda;
+#pragma unroll
+      for (int i = 0; i < 24; ++i) {
+        const int k = kb0 * 8 + i;
+        xin[i] = (i < 8 * nkb && row < p.mp.rows && k < p.k_total) ? __ldg(arow + k) : 0.0f;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        if (q < nkb) {
+          __align__(16) __nv_bfloat16 h8[8], m8[8], l8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = (kb0 + q) * 8 + i;
+            const float x = (row < p.mp.rows && k < p.k_total) ? mel_in_value(xin[8 * q + i], p.in_kind, p.mp) : 0.0f;
+            h8[i] = __float2bfloat16_rn(x);
+            const float r1 = x - __bfloat162float(h8[i]);
+            m8[i] = __float2bfloat16_rn(r1);
+            l8[i] = __float2bfloat16_rn(r1 - __bfloat162float(m8[i]));
+          }
+          const uint32_t off = (uint32_t)(kb0 + q) * kLbo + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+          *reinterpret_cast<uint4*>(smF + off) = *reinterpret_cast<const uint4*>(h8);
+          *reinterpret_cast<uint4*>(smF + kT2PartBytes + off) = *reinterpret_cast<const uint4*>(m8);
+          *reinterpret_cast<uint4*>(smF + 2 * kT2PartBytes + off) = *reinterpret_cast<const uint4*>(l8);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+    }
+    auto load_tile = [&](int bt, uint32_t nt) {                      // pseudo-inverse rows of bin tile bt -> buffer nt & 1
+      const uint32_t b = nt & 1u;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.b) + (size_t)bt * kT2TileBytes;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * b), "r"(kT2TileBytes) : "memory");
+      // several copies in flight instead of one 60 KB copy (the copy engine works a single request off sequentially)
+      constexpr uint32_t kPiece = kT2TileBytes / kT2Pieces;
+#pragma unroll
+      for (uint32_t i = 0; i < (uint32_t)kT2Pieces; ++i)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smP_addr + b * kT2TileBytes + i * kPiece), "l"(src + i * kPiece), "r"(kPiece), "r"(bar0 + 8 * b) : "memory");
+    };
+    // buffer nt & 1 is free once the MMAs of pair nt - 2 are complete (accumulator-full barrier of that pair)
+    auto wait_buffer_free = [&](uint32_t nt) {
+      if (nt >= 2) mbar_wait(bar0 + 16 + 8 * (nt & 1u), ((nt - 2) >> 1) & 1u);
+    };
+    if (producer && lane == 0) {                                     // the first tile streams in behind the conversion
+      wait_buffer_free(n_tile);
+      load_tile(0, n_tile);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                                 // the frame operand is in place
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    if (producer) {
+      if (lane == 0) {
+        for (int bt = 0; bt < kT2Tiles; ++bt) {
+          const uint32_t nt = n_tile + (uint32_t)bt, b = nt & 1u, use = nt >> 1;
+          if (bt + 1 < kT2Tiles) { wait_buffer_free(nt + 1); load_tile(bt + 1, nt + 1); }
+          mbar_wait(bar0 + 8 * b, use & 1u);                         // the tile has landed
+          if (use >= 1) mbar_wait(bar0 + 32 + 8 * b, (use - 1) & 1u);  // the accumulator's previous contents are drained
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int pa[6] = {0, 0, 1, 0, 1, 2};                      // (pinv part, frame part): hi*hi, hi*mid, mid*hi, hi*lo, mid*mid, lo*hi
+          const int pb[6] = {0, 1, 0, 2, 1, 0};
+          const uint32_t abase = smP_addr + b * kT2TileBytes;
+          const uint32_t dcol = tmem_base + b * (uint32_t)kT2Frames;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+#pragma unroll
+            for (int j = 0; j < kTcKSteps; ++j) {
+              const uint64_t da = umma_smem_desc(abase + pa[c] * kT2PartBytes + 2 * j * kLbo, kLbo, 128);
+              const uint64_t db = umma_smem_desc(smF_addr + pb[c] * kT2PartBytes + 2 * j * kLbo, kLbo, 128);
+              umma_bf16(dcol, da, db, kIdesc, (c | j) != 0 ? 1u : 0u);
+            }
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 16 + 8 * b) : "memory");
+        }
+      }
+      __syncwarp();
+    } else {
+      // ---- epilogue warps: TMEM lane group = warp % 4 (bins), 32 frames = warp / 4
+      const int lane_base = (warp & 3) * 32, fq = warp >> 2;
+      // (kernel parameters read once: inside the unrolled store loop each use was a constant-bank load on the critical path)
+      const int ldo = p.ldo, n_valid = p.n_valid;
+      const long long n_rows = p.mp.rows;
+      const bool do_power = p.out_kind == 1;
+      const float power = p.mp.power;
+      for (int bt = 0; bt < kT2Tiles; ++bt) {
+        const uint32_t nt = n_tile + (uint32_t)bt, b = nt & 1u, use = nt >> 1;
+        mbar_wait(bar0 + 16 + 8 * b, use & 1u);                      // the MMAs of this pair are complete
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[32];
+        tmem_ld32<0>(tmem_base + ((uint32_t)lane_base << 16) + b * (uint32_t)kT2Frames + 32u * (uint32_t)fq, v);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 32 + 8 * b) : "memory");   // drained
+        const int bin = bt * kT2Bins + lane_base + lane;
+        if (bin < n_valid) {
+          float* o = p.out + (row0 + 32 * fq) * ldo + bin;
+          const int nrows = (int)min((long long)32, n_rows - (row0 + 32 * fq));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = fmaxf(1e-10f, __uint_as_float(v[j]));
+            if (do_power) {
+              if (pow15) {                         // x ** 1.5 (the shipped `power`): x * sqrt(x), sqrt.approx is ~1 ulp
+                float sq;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(x));
+                x *= sq;
+              } else {
+                x = exp2f(power * log2f(x));
+              }
+            }
+            if (j < nrows) *o = x;
+            o += ldo;
+          }
+        }
+      }
+    }
+    n_tile += (uint32_t)kT2Tiles;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+}  // namespace ttsa

@@ -66,7 +66,7 @@ struct ttsa_plan {
   int nz = 32;                     // compile-time zero-pruning class of the frame kernels (20 or 32)
   int ctas_per_sm = 1;
   int debug = 0;                   // profiling builds only (TTSA_PROFILE_BUILD + env TTSA_DEBUG): skip phases of the tile kernel
-  int mel_gemm = 0;                // TTSA_MEL_GEMM: 0 default (tensor cores), 1 "simt", 2 "tc_simple"
+  int mel_gemm = 0;                // TTSA_MEL_GEMM: 0 default (tensor cores, transposed kernel), 1 "simt", 2 "tc_simple", 3 "tc96" (round-1 pipelined kernel)
   bool generic = false;            // n_fft != 2048: the any-size kernels of generic_kernels.cuh
   GenGeo gg;
   GenTables gt;
@@ -83,6 +83,7 @@ struct ttsa_plan {
   // tensor-core operands: B matrices pre-split into 3 bf16 terms in the canonical UMMA layout (mel_gemm_tc.cuh)
   const __nv_bfloat16* d_pinv_tc = nullptr;   // pinv: [5 n-tiles of 208 bins][chunks][3][208 x 80]
   const __nv_bfloat16* d_mel_tc = nullptr;    // mel basis (num_mels == 80 only): [1][13 chunks][3][80 x 80]
+  const __nv_bfloat16* d_pinv_tc128 = nullptr; // pinv for the transposed kernel (num_mels <= 80): [9 bin tiles of 128][3][128 x 80]
   const __nv_bfloat16* d_pinv_tc96 = nullptr; // pinv for the pipelined kernel (num_mels <= 80): [11 n-tiles of 96][3][96 x 80]
   int pinv_chunks = 0;
 };
@@ -587,6 +588,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   if (c.num_mels == 80) h_mel_tc = canon_split_b(p->h_mel, 80, kF, 80, 1, 13);
   std::vector<uint16_t> h_pinv_tc96;
   if (p->pinv_chunks == 1) h_pinv_tc96 = canon_split_b(p->h_inv_mel, kF, c.num_mels, kM2lN, kM2lTiles, 1);
+  std::vector<uint16_t> h_pinv_tc128;
+  if (p->pinv_chunks == 1) h_pinv_tc128 = canon_split_b(p->h_inv_mel, kF, c.num_mels, kT2Bins, kT2Tiles, 1);
   // one device block
   struct Piece { const void* src; size_t bytes; size_t off; };
   std::vector<Piece> pieces = {
@@ -598,7 +601,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}, {h_img.data(), h_img.size() * 4, 0},
       {h_melc.data(), h_melc.size() * 4, 0}, {h_pw2.data(), h_pw2.size() * 4, 0}, {h_wps.data(), h_wps.size() * 4, 0},
       {h_edge_head.data(), h_edge_head.size() * 4, 0}, {h_edge_tail.data(), h_edge_tail.size() * 4, 0},
-      {h_msched.data(), h_msched.size() * 4, 0}};
+      {h_msched.data(), h_msched.size() * 4, 0}, {h_pinv_tc128.data(), h_pinv_tc128.size() * 2, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -617,6 +620,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->d_pinv_tc = (const __nv_bfloat16*)(base + pieces[11].off);
   p->d_mel_tc = h_mel_tc.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[12].off);
   p->d_pinv_tc96 = h_pinv_tc96.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[13].off);
+  p->d_pinv_tc128 = h_pinv_tc128.empty() ? nullptr : (const __nv_bfloat16*)(base + pieces[21].off);
   p->tb.smem_image = (const float*)(base + pieces[14].off);
   p->tb.mel_compact = (const float*)(base + pieces[15].off);
   p->tb.wE = (const float*)(base + pieces[2].off);
@@ -665,7 +669,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   { const char* dbg = std::getenv("TTSA_DEBUG"); p->debug = dbg ? std::atoi(dbg) : 0; }
 #endif
   { const char* mg = std::getenv("TTSA_MEL_GEMM");
-    p->mel_gemm = mg == nullptr ? 0 : (std::strcmp(mg, "simt") == 0 ? 1 : (std::strcmp(mg, "tc_simple") == 0 ? 2 : 0)); }
+    p->mel_gemm = mg == nullptr ? 0 : (std::strcmp(mg, "simt") == 0 ? 1 : (std::strcmp(mg, "tc_simple") == 0 ? 2 : (std::strcmp(mg, "tc96") == 0 ? 3 : 0))); }
   cudaError_t e = cudaFuncSetAttribute(mel_to_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kMtlMaxK * (kMtlBins + kMtlRows) * 4);
   if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "mel kernel configuration: %s", cudaGetErrorString(e)); }
@@ -673,6 +677,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(gemm_bf16x3_tc_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kTcRows * kTcChunk * 2 + 3 * 80 * kTcChunk * 2);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mel_to_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kM2lSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mel_to_linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kT2Smem);
   if (e != cudaSuccess) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "tensor-core GEMM configuration: %s", cudaGetErrorString(e)); }
   *out = p;
   return TTSA_OK;
@@ -1287,6 +1292,15 @@ extern "C" int ttsa_mel_to_linear(const ttsa_plan* plan, const ttsa_batch* batch
     dim3 grid((mp.F + kMtlBins - 1) / kMtlBins, (unsigned)((batch->total_frames + kMtlRows - 1) / kMtlRows));
     const size_t smem = (size_t)mp.num_mels * (kMtlBins + kMtlRows) * 4;
     mel_to_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mp, plan->d_pinvT, plan->ldp, mel_dev, lin_out_dev, in_kind, out_kind);
+  } else if (plan->d_pinv_tc128 != nullptr && plan->mel_gemm == 0) {
+    // transposed, warp-specialised tensor-core kernel: bins as the UMMA M dimension, coalesced stores from registers
+    TcGemmParams tp;
+    tp.mp = mp; tp.a = mel_dev; tp.lda = mp.num_mels; tp.k_total = mp.num_mels; tp.n_chunks = 1;
+    tp.b = plan->d_pinv_tc128; tp.out = lin_out_dev; tp.ldo = kF; tp.n_valid = kF; tp.in_kind = in_kind; tp.out_kind = out_kind;
+    tp.mode = 0;
+    const int n_ftiles = (int)((batch->total_frames + kT2Frames - 1) / kT2Frames);
+    const int grid = n_ftiles < plan->num_sms ? n_ftiles : plan->num_sms;
+    mel_to_linear_tc2_kernel<<<grid, kT2Threads, kT2Smem, (cudaStream_t)stream>>>(tp, n_ftiles);
   } else if (plan->d_pinv_tc96 != nullptr && plan->mel_gemm != 2) {
     // pipelined tensor-core kernel: one CTA per 128-frame tile walks all bin tiles
     TcGemmParams tp;
