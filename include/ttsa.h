@@ -91,6 +91,13 @@ int ttsa_plan_destroy(ttsa_plan* plan);
 int ttsa_plan_mel_basis(const ttsa_plan* plan, double* host_out);
 /* np.linalg.pinv(_build_mel_basis()) (utils/audio.py:65): float64 [num_freq, num_mels], HOST buffer. */
 int ttsa_plan_inv_mel_basis(const ttsa_plan* plan, double* host_out);
+/* The schedule by which the feature kernel contracts |X| with _build_mel_basis() (_linear_to_mel inside
+ * melspectrogram, utils/audio.py:60-62,145-152), for inspection and tests; works on host-only plans.
+ * pairs_out[3]: step pairs of the three slots (all 0: this basis is served by the per-filter lane schedule);
+ * words_out (HOST, may be NULL): float4 [NP][32] | u32 [NP][32] | u32 [3][32] as described in
+ * csrc/host_tables.hpp (mel_segment_schedule).  Returns the number of 32-bit words (<= cap_words when
+ * words_out is given) or a negative ttsa_status. */
+int64_t ttsa_plan_mel_schedule(const ttsa_plan* plan, int32_t* pairs_out, uint32_t* words_out, int64_t cap_words);
 
 /* ---- batch layout ----------------------------------------------------------------------- */
 /* From per-utterance frame counts T[u] (spectrogram-domain inputs; the waveform of utterance u then

@@ -193,3 +193,74 @@ def test_pinv_follows_numpy_svd_and_moore_penrose():
         np.testing.assert_allclose(P, Pref, atol=1e-9 * np.abs(Pref).max())
         np.testing.assert_allclose(M @ P @ M, M, atol=1e-10 * np.abs(M).max())
         np.testing.assert_allclose(P @ M @ P, P, atol=1e-10 * np.abs(P).max())
+
+
+def _run_mel_schedule(pairs, words, mag):
+    """Numpy restatement of the feature kernel's mel stage on the segment schedule (feat_stream.cuh): three slots of
+    (falling, rising) accumulators per lane, then <= 4 partial sums per filter through the 193-entry scratch row."""
+    npairs = int(sum(pairs))
+    w = words[:128 * npairs].view(np.float32).reshape(npairs, 32, 4).astype(np.float64)
+    ix = words[128 * npairs:160 * npairs].reshape(npairs, 32)
+    comb = words[160 * npairs:160 * npairs + 96].reshape(3, 32)
+    assert np.all((ix & 0xffff) % 4 == 0) and np.all((ix >> 16) % 4 == 0)
+    ba, bb = (ix & 0xffff) // 4, (ix >> 16) // 4
+    assert ba.max() < mag.size and bb.max() < mag.size
+    part = np.zeros(193)
+    pr = 0
+    conflicts = 0
+    for sl in range(3):
+        accd, accu = np.zeros(32), np.zeros(32)
+        for _ in range(int(pairs[sl])):
+            for b in (ba[pr], bb[pr]):
+                conflicts += 32 - len(set((b % 32).tolist()))
+            accd += w[pr, :, 0] * mag[ba[pr]] + w[pr, :, 2] * mag[bb[pr]]
+            accu += w[pr, :, 1] * mag[ba[pr]] + w[pr, :, 3] * mag[bb[pr]]
+            pr += 1
+        part[2 * (32 * sl + np.arange(32))] = accd
+        part[2 * (32 * sl + np.arange(32)) + 1] = accu
+    out = np.zeros(96)
+    for r in range(3):
+        c = comb[r]
+        out[32 * r:32 * r + 32] = part[c & 255] + part[(c >> 8) & 255] + part[(c >> 16) & 255] + part[c >> 24]
+    return out, conflicts
+
+
+@pytest.mark.parametrize("audio", [MAIN_AUDIO, TEST_AUDIO, dict(MAIN_AUDIO, sample_rate=16000), dict(MAIN_AUDIO, num_mels=90),
+                                   dict(MAIN_AUDIO, num_mels=40, mel_fmin=95.0, mel_fmax=7600.0),
+                                   dict(MAIN_AUDIO, sample_rate=24000, mel_fmax=None, mel_fmin=50.0)])
+def test_mel_segment_schedule_reproduces_the_basis(audio):
+    """The schedule the warp-stream feature kernel walks (ttsa_plan_mel_schedule; _linear_to_mel inside melspectrogram,
+    utils/audio.py:60-62) is the float32 mel basis exactly: every tap appears once, filters are sums of their partial sums."""
+    ap, plan = _host_plan(audio)
+    pairs = (ctypes.c_int32 * 3)()
+    n = plan.lib.ttsa_plan_mel_schedule(plan.handle, pairs, None, 0)
+    assert n > 0, "a Slaney triangular bank must get the segment schedule"
+    words = np.zeros(n, dtype=np.uint32)
+    assert plan.lib.ttsa_plan_mel_schedule(plan.handle, pairs, words.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), n) == n
+    pairs = [int(x) for x in pairs]
+    assert n == 160 * sum(pairs) + 96 and pairs[0] >= pairs[1] >= pairs[2] >= 0
+    basis32 = ap._build_mel_basis().astype(np.float32).astype(np.float64)
+    nm = audio["num_mels"]
+    # unit magnitudes recover every row sum, one-hot magnitudes every single tap
+    rng = np.random.default_rng(3)
+    for mag in (np.ones(1025), rng.random(1025) * 10.0 ** rng.uniform(-4, 2, 1025)):
+        out, conflicts = _run_mel_schedule(pairs, words, mag)
+        ref = basis32 @ mag
+        np.testing.assert_allclose(out[:nm], ref, rtol=1e-12, atol=1e-300)
+        assert np.all(out[nm:] == 0.0)
+        assert conflicts <= 0.05 * 64 * sum(pairs)      # bank conflicts among the 32 magnitude reads of a step
+    for k in rng.integers(0, 1025, 40):
+        mag = np.zeros(1025); mag[k] = 1.0
+        out, _ = _run_mel_schedule(pairs, words, mag)
+        np.testing.assert_array_equal(out[:nm], basis32[:, k])
+    # the schedule is shorter than a per-filter walk: about one step per bin of the bank and lane
+    nz_bins = int(np.count_nonzero(basis32.any(axis=0)))
+    assert 2 * sum(pairs) <= 1.5 * nz_bins / 32 + 8, (pairs, nz_bins)
+
+
+def test_mel_segment_schedule_declines_what_it_cannot_hold():
+    """More segments than the 96 (slot, lane) cells: no schedule, the feature kernel keeps the per-filter lane schedule."""
+    ap, plan = _host_plan(dict(MAIN_AUDIO, num_mels=96))
+    pairs = (ctypes.c_int32 * 3)(7, 7, 7)
+    assert plan.lib.ttsa_plan_mel_schedule(plan.handle, pairs, None, 0) == 0
+    assert list(pairs) == [0, 0, 0]

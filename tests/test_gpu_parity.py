@@ -630,8 +630,9 @@ def test_feature_stream_kernel_ragged_vs_oracle_and_tile(monkeypatch, sr, pre):
     lens = [9000, 1, 551, 2300, 40000, 275, 1103, 6000, 2209]
     wavs = [synth_speech_like(300 + i, n_samples=n) for i, n in enumerate(lens)]
     res = {}
-    for kernel in ("stream", "tile"):
-        monkeypatch.setenv("TTSA_FEAT_KERNEL", kernel)
+    for kernel in ("stream", "lane", "tile"):     # "lane": the stream kernel with the per-filter lane schedule of the mel basis
+        monkeypatch.setenv("TTSA_FEAT_KERNEL", "tile" if kernel == "tile" else "stream")
+        monkeypatch.setenv("TTSA_FEAT_MEL", "lane" if kernel == "lane" else "seg")
         monkeypatch.setenv("TTSA_FEAT_MINFRAMES", "0")
         monkeypatch.setenv("TTSA_WPS_GRID", "2")
         A._PLAN_CACHE.clear()
@@ -642,7 +643,7 @@ def test_feature_stream_kernel_ragged_vs_oracle_and_tile(monkeypatch, sr, pre):
         _, mel_only = ap.features_batch(buf, lay, want_linear=False)
         assert torch.equal(lin, lin_only) and torch.equal(mel, mel_only)
         res[kernel] = ([x.cpu().numpy().copy() for x in lay.split_frames(lin)], [x.cpu().numpy().copy() for x in lay.split_frames(mel)])
-    for k in ("TTSA_FEAT_KERNEL", "TTSA_FEAT_MINFRAMES", "TTSA_WPS_GRID"):
+    for k in ("TTSA_FEAT_KERNEL", "TTSA_FEAT_MEL", "TTSA_FEAT_MINFRAMES", "TTSA_WPS_GRID"):
         monkeypatch.delenv(k)
     A._PLAN_CACHE.clear()
     ap = _ap(audio)
@@ -657,6 +658,10 @@ def test_feature_stream_kernel_ragged_vs_oracle_and_tile(monkeypatch, sr, pre):
         assert np.mean(np.abs(m - mo) <= FWD_TOL) >= 0.99 and np.all(np.abs(m - mo) <= _db_tol(ap, Dm.T, Dm.max(axis=1)).T), (sr, pre, u)
         lt, mt = res["tile"][0][u], res["tile"][1][u]
         assert np.mean(np.abs(l - lt) <= FWD_TOL) >= 0.99 and np.mean(np.abs(m - mt) <= FWD_TOL) >= 0.99, (sr, pre, u)
+        # the two mel schedules of the stream kernel: the same taps in another order; the linear output is the same code
+        ll, ml = res["lane"][0][u], res["lane"][1][u]
+        assert np.array_equal(l, ll), (sr, pre, u)
+        assert np.all(np.abs(ml - mo) <= _db_tol(ap, Dm.T, Dm.max(axis=1)).T) and np.mean(np.abs(m - ml) <= FWD_TOL) >= 0.99, (sr, pre, u)
 
 
 # ------------------------------------------------------------------------------------------------ post-processing

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "ttsa_plan_destroy": (c_int, [c_void_p]),
     "ttsa_plan_mel_basis": (c_int, [c_void_p, POINTER(c_double)]),
     "ttsa_plan_inv_mel_basis": (c_int, [c_void_p, POINTER(c_double)]),
+    "ttsa_plan_mel_schedule": (c_int64, [c_void_p, POINTER(c_int32), POINTER(c_uint32), c_int64]),
     "ttsa_batch_from_frames": (c_int, [c_void_p, POINTER(c_int32), c_int32, POINTER(c_void_p)]),
     "ttsa_batch_from_wav_lengths": (c_int, [c_void_p, POINTER(c_int32), c_int32, POINTER(c_void_p)]),
     "ttsa_batch_from_frames_strided": (c_int, [c_void_p, POINTER(c_int32), c_int32, c_int64, POINTER(c_void_p)]),

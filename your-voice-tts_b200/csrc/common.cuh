@@ -67,6 +67,8 @@ struct Geo {
   int mel_smem_floats;       // > 0: the compact mel basis (Tables::mel_compact) fits behind Layout::sm_total in the
                              //      feature kernel's shared memory; 0: read the banded basis from global memory
   int mel_steps;             // > 0: steps of the lane schedule (Tables::mel_sched) of the warp-stream feature kernel
+  int mel_seg_pairs[3];      // [0] > 0: the segment schedule (Tables::mel_seg) serves the warp-stream feature kernel instead:
+                             //      step pairs of its three slots (host_tables.hpp, mel_segment_schedule)
   // spectrogram value -> magnitude:  S = exp2(c1 * clip(x, lo, hi) + c0)   (denormalize, +ref, db_to_amp, **power fused)
   float s_c1, s_c0, s_lo, s_hi;
   // amplitude -> normalised dB:      v = clip(n_a * log2(max(min_amp, a)) + n_b, n_lo, n_hi)
@@ -98,6 +100,8 @@ struct Tables {
   const float* mel_compact;
   // lane schedule of the same basis for feat_stream.cuh: float4 (w0, w1, w2, bin) [Geo::mel_steps][32], then int [3][32] filter ids
   const float* mel_sched;
+  // segment schedule (host_tables.hpp, MelSegSchedule::words): float4 [NP][32] | u32 [NP][32] | u32 [3][32]
+  const unsigned* mel_seg;
 };
 
 // Batch layout on the device.
@@ -119,6 +123,12 @@ struct BatchDev {
 #endif
 constexpr int kWpsWinStride = 20;           // floats per lane row of the warp-stream kernel's window tables (>= rows of a frame; stride / 4 odd)
 constexpr int kWpsWarps = TTSA_WPS_WARPS;   // warps per CTA (one CTA per SM) of the warp-stream Griffin-Lim kernel
+constexpr int kMelSegScratch = 196;         // floats per warp: 192 partial sums of the segment schedule, the zero cell, padding
+// floats of the mel schedule (or compact basis) the warp-stream feature kernel keeps in shared memory
+__host__ __device__ inline int feat_mel_floats(const Geo& g) {
+  if (g.mel_seg_pairs[0] > 0) return 160 * (g.mel_seg_pairs[0] + g.mel_seg_pairs[1] + g.mel_seg_pairs[2]) + 96 + kWpsWarps * kMelSegScratch;
+  return g.mel_steps > 0 ? g.mel_steps * 128 + 96 : g.mel_smem_floats;
+}
 
 // Work partition of the warp-stream Griffin-Lim kernel (gl_stream.cuh), built by the host with the batch.
 struct WpsDev {

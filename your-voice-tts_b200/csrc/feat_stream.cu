@@ -9,7 +9,7 @@ static const char* launch_one(int grid, cudaStream_t st, const Geo& g, const Tab
                               int total_frames) {
   if constexpr (!FeatGeo<HOP, WIN>::kFits) return "feat_stream: geometry does not fit shared memory";
   else {
-    const size_t mel_floats = g.mel_steps > 0 ? (size_t)g.mel_steps * 128 + 96 : (size_t)g.mel_smem_floats;
+    const size_t mel_floats = (size_t)feat_mel_floats(g);
     const size_t smem = ((size_t)FeatGeo<HOP, WIN>::sm_mel + (a.mel_out != nullptr ? mel_floats : 0)) * 4;
     if (a.lin_out != nullptr && a.mel_out != nullptr) feat_stream_kernel<HOP, WIN, true, true><<<grid, kWpsThreads, smem, st>>>(g, tb, bd, a, total_frames);
     else if (a.lin_out != nullptr) feat_stream_kernel<HOP, WIN, true, false><<<grid, kWpsThreads, smem, st>>>(g, tb, bd, a, total_frames);

@@ -65,7 +65,12 @@ feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameA
                  ::"r"(dst), "l"(tb.wps_image), "r"(bytes), "r"(mbar) : "memory");
   }
   if (MEL) {
-    if (g.mel_steps > 0) for (int i = tid; i < g.mel_steps * 128 + 96; i += kWpsThreads) smem[FG::sm_mel + i] = tb.mel_sched[i];
+    if (g.mel_seg_pairs[0] > 0) {
+      const int nw_ = 160 * (g.mel_seg_pairs[0] + g.mel_seg_pairs[1] + g.mel_seg_pairs[2]) + 96;
+      unsigned* const d = reinterpret_cast<unsigned*>(smem + FG::sm_mel);
+      for (int i = tid; i < nw_; i += kWpsThreads) d[i] = tb.mel_seg[i];
+      if (lane == 0) smem[FG::sm_mel + nw_ + warp * kMelSegScratch + 192] = 0.0f;      // the zero cell of this warp's scratch row
+    } else if (g.mel_steps > 0) for (int i = tid; i < g.mel_steps * 128 + 96; i += kWpsThreads) smem[FG::sm_mel + i] = tb.mel_sched[i];
     else for (int i = tid; i < g.mel_smem_floats; i += kWpsThreads) smem[FG::sm_mel + i] = tb.mel_compact[i];
   }
   __syncthreads();
@@ -285,7 +290,40 @@ feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameA
       if (want_mel) {
         __syncwarp();
         float* const out = a.mel_out + row * g.num_mels;
-        if (g.mel_steps > 0) {
+        if (g.mel_seg_pairs[0] > 0) {
+          // segment schedule (host_tables.hpp, mel_segment_schedule): every bin is read once and feeds the falling tap of one
+          // filter and the rising tap of the next; three slots of cells, then <= 4 partial sums per filter through the scratch row
+          const int np_ = g.mel_seg_pairs[0] + g.mel_seg_pairs[1] + g.mel_seg_pairs[2];
+          const float4* const wq = reinterpret_cast<const float4*>(smem + FG::sm_mel) + lane;
+          const unsigned* const iq = reinterpret_cast<const unsigned*>(smem + FG::sm_mel + 128 * np_) + lane;
+          const unsigned* const comb = iq + 32 * np_;
+          float* const part = smem + FG::sm_mel + 160 * np_ + 96 + warp * kMelSegScratch;
+          const char* const mb = reinterpret_cast<const char*>(magbuf);
+          int pr = 0;
+#pragma unroll
+          for (int sl = 0; sl < 3; ++sl) {
+            float accd = 0.0f, accu = 0.0f;
+            const int pend = pr + g.mel_seg_pairs[sl];
+#pragma unroll 4
+            for (; pr < pend; ++pr) {
+              const float4 w = wq[32 * pr];
+              const unsigned ix = iq[32 * pr];
+              const float ma = *reinterpret_cast<const float*>(mb + (ix & 0xffffu));
+              const float mg = *reinterpret_cast<const float*>(mb + (ix >> 16));
+              accd = fmaf(w.x, ma, accd); accu = fmaf(w.y, ma, accu);
+              accd = fmaf(w.z, mg, accd); accu = fmaf(w.w, mg, accu);
+            }
+            *reinterpret_cast<float2*>(part + 2 * (32 * sl + lane)) = make_float2(accd, accu);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const unsigned cw = comb[32 * r];
+            const float sum = ((part[cw & 255u] + part[(cw >> 8) & 255u]) + part[(cw >> 16) & 255u]) + part[cw >> 24];
+            const float v = amp_to_norm_db(sum, g);
+            if (32 * r + lane < g.num_mels) out[32 * r + lane] = v;
+          }
+        } else if (g.mel_steps > 0) {
           // lane schedule (built by the host with the plan): up to three filters per lane, about sum(taps) / 32 steps, the 32
           // magnitude reads of a step in 32 different banks; one 16-byte load, one magnitude load, three FMAs per step
           const float4* const sch = reinterpret_cast<const float4*>(smem + FG::sm_mel) + lane;

@@ -4,6 +4,8 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
+#include <cstring>
 #include <vector>
 
 namespace ttsa_host {
@@ -106,6 +108,139 @@ inline std::vector<double> pinv_wide(const std::vector<double>& M, int m, int n)
     }
   }
   return P;
+}
+
+// Segment schedule of a banded (triangular, 50 % overlap) mel basis for the warp-stream feature kernel (feat_stream.cuh).
+// A bin between the peaks of filters s and s + 1 has (at most) two taps: a falling one for filter s, a rising one for s + 1.
+// The bins are grouped by that s ("segments", s = -1 .. num_mels - 1), long segments are split into pieces, and every piece
+// becomes one (slot, lane) CELL, slot = 0..2: the lane reads each of its bins ONCE and feeds two accumulators (D: falling tap
+// -> filter s, U: rising tap -> filter s + 1), so a step moves 8 bytes of weights where a per-filter walk moves a tap per
+// filter and bin.  The three slots run back to back with trip counts common to the warp (cells sorted by size, so a slot is as
+// long as its largest cell); inside a slot the order in which a lane walks its bins is chosen so that the 32 lanes of a step
+// read 32 different banks of the magnitude row.  Filter j is the sum of <= 4 partial sums (D of the cells of segment j, U of
+// those of segment j - 1), combined through a 193-float scratch row per warp.
+//   words: float4 [NP][32]  (wD_a, wU_a, wD_b, wU_b)      two steps per entry (a, b), NP = pairs[0] + pairs[1] + pairs[2]
+//          u32    [NP][32]  byte offset of bin a | byte offset of bin b << 16
+//          u32    [3][32]   four scratch indices (one byte each; 2 cell + {0: D, 1: U}; 192: the zero cell) of filter 32 r + lane
+struct MelSegSchedule {
+  bool ok = false;
+  int pairs[3] = {0, 0, 0};
+  std::vector<uint32_t> words;
+};
+
+inline MelSegSchedule mel_segment_schedule(const std::vector<double>& mel, int num_mels, int F) {
+  MelSegSchedule out;
+  if (num_mels < 1 || num_mels > 96 || F < 32 || F > 16000) return out;
+  struct Tap { int bin; float wd, wu; };
+  std::vector<std::vector<Tap>> seg(num_mels + 1);                 // seg[s + 1]: bins between the peaks of filters s and s + 1
+  std::vector<int> peak(num_mels, 0);
+  for (int m = 0; m < num_mels; ++m)
+    for (int k = 1; k < F; ++k)
+      if (mel[(size_t)m * F + k] > mel[(size_t)m * F + peak[m]]) peak[m] = k;
+  for (int k = 0; k < F; ++k) {
+    int f0 = -1, f1 = -1, cnt = 0;
+    for (int m = 0; m < num_mels; ++m)
+      if ((float)mel[(size_t)m * F + k] != 0.0f) { if (cnt == 0) f0 = m; else f1 = m; ++cnt; }
+    if (cnt == 0) continue;
+    if (cnt > 2 || (cnt == 2 && f1 != f0 + 1)) return out;         // not a 50 %-overlap bank: the lane schedule serves it
+    const float w0 = (float)mel[(size_t)f0 * F + k];
+    int s; Tap t{k, 0.f, 0.f};
+    if (cnt == 2) { s = f0; t.wd = w0; t.wu = (float)mel[(size_t)f1 * F + k]; }
+    else if (k > peak[f0]) { s = f0; t.wd = w0; }                  // only the falling side of f0 (the next filter starts later)
+    else { s = f0 - 1; t.wu = w0; }                                // only its rising side (or its peak)
+    seg[s + 1].push_back(t);
+  }
+  // split: the piece length that gives the fewest steps with <= 96 cells and <= 4 partial sums per filter
+  size_t longest = 1;
+  for (auto& sg : seg) longest = std::max(longest, sg.size());
+  auto n_pieces = [&](size_t n, size_t C) { return (n + C - 1) / C; };
+  size_t best_c = 0, best_steps = ~(size_t)0;
+  for (size_t C = 2; C <= longest + 1; ++C) {
+    std::vector<size_t> sizes;
+    bool fits = true;
+    for (int s = 0; s <= num_mels; ++s) {
+      const size_t q = n_pieces(seg[s].size(), C);
+      for (size_t i = 0; i < q; ++i) sizes.push_back(seg[s].size() / q + (i < seg[s].size() % q ? 1 : 0));
+      if (s > 0 && q + n_pieces(seg[s - 1].size(), C) > 4) fits = false;
+    }
+    if (!fits || sizes.size() > 96) continue;
+    std::sort(sizes.begin(), sizes.end(), [](size_t a, size_t b) { return a > b; });
+    size_t steps = 0;
+    for (size_t sl = 0; sl < 3; ++sl) if (sizes.size() > 32 * sl) steps += (sizes[32 * sl] + 1) / 2 * 2;
+    if (steps < best_steps) { best_steps = steps; best_c = C; }
+  }
+  if (best_c == 0) return out;
+  struct Cell { int s; std::vector<Tap> taps; };
+  std::vector<Cell> cells;
+  for (int s = 0; s <= num_mels; ++s) {
+    const size_t n = seg[s].size(), q = n_pieces(n, best_c);
+    size_t at = 0;
+    for (size_t i = 0; i < q; ++i) {
+      const size_t len = n / q + (i < n % q ? 1 : 0);
+      cells.push_back({s - 1, std::vector<Tap>(seg[s].begin() + at, seg[s].begin() + at + len)});
+      at += len;
+    }
+  }
+  std::stable_sort(cells.begin(), cells.end(), [](const Cell& a, const Cell& b) { return a.taps.size() > b.taps.size(); });
+  int first_pair[3] = {0, 0, 0}, np = 0;
+  for (int sl = 0; sl < 3; ++sl) {
+    first_pair[sl] = np;
+    out.pairs[sl] = cells.size() > (size_t)32 * sl ? (int)((cells[32 * sl].taps.size() + 1) / 2) : 0;
+    np += out.pairs[sl];
+  }
+  out.words.assign((size_t)160 * np + 96, 0u);
+  auto put_f = [&](size_t i, float v) { uint32_t u; std::memcpy(&u, &v, 4); out.words[i] = u; };
+  for (int sl = 0; sl < 3; ++sl) {
+    const int steps = 2 * out.pairs[sl];
+    std::vector<std::vector<char>> done(32);
+    std::vector<int> left(32, 0);
+    for (int l = 0; l < 32; ++l) {
+      const size_t c = (size_t)32 * sl + l;
+      if (c < cells.size()) { done[l].assign(cells[c].taps.size(), 0); left[l] = (int)cells[c].taps.size(); }
+    }
+    for (int st = 0; st < steps; ++st) {
+      unsigned used = 0;                                            // banks read in this step
+      std::vector<int> lanes(32);
+      for (int l = 0; l < 32; ++l) lanes[l] = l;
+      std::stable_sort(lanes.begin(), lanes.end(), [&](int x, int y) { return left[x] > left[y]; });   // lanes without slack choose first
+      for (int l : lanes) {
+        const size_t c = (size_t)32 * sl + l;
+        int pick = -1;
+        if (left[l] > 0) {
+          const std::vector<Tap>& tp = cells[c].taps;
+          for (size_t i = 0; i < tp.size(); ++i)
+            if (!done[l][i] && !(used >> (tp[i].bin & 31) & 1u)) { pick = (int)i; break; }
+          if (pick < 0 && left[l] >= steps - st)
+            for (size_t i = 0; i < tp.size(); ++i) if (!done[l][i]) { pick = (int)i; break; }           // a bank conflict
+        }
+        int bin = 0; float wd = 0.f, wu = 0.f;
+        if (pick >= 0) {
+          const Tap& t = cells[c].taps[pick];
+          done[l][pick] = 1; --left[l];
+          bin = t.bin; wd = t.wd; wu = t.wu;
+        } else {                                                    // idle step: zero weights, a bin in a free bank
+          for (int b = 0; b < 32; ++b) if (!(used >> b & 1u)) { bin = b; break; }
+        }
+        used |= 1u << (bin & 31);
+        const size_t pr = (size_t)first_pair[sl] + st / 2, h = st & 1;
+        put_f((pr * 32 + l) * 4 + 2 * h, wd);
+        put_f((pr * 32 + l) * 4 + 2 * h + 1, wu);
+        out.words[(size_t)128 * np + pr * 32 + l] |= (uint32_t)(bin * 4) << (16 * h);
+      }
+    }
+    for (int l = 0; l < 32; ++l) if (left[l] != 0) return out;
+  }
+  for (int j = 0; j < 96; ++j) {
+    uint32_t w = 0; int n = 0;
+    for (size_t c = 0; c < cells.size() && j < num_mels; ++c) {
+      if (cells[c].s == j && n < 4) w |= (uint32_t)(2 * c) << (8 * n++);
+      if (cells[c].s == j - 1 && n < 4) w |= (uint32_t)(2 * c + 1) << (8 * n++);
+    }
+    for (; n < 4; ++n) w |= 192u << (8 * n);
+    out.words[(size_t)160 * np + j] = w;
+  }
+  out.ok = true;
+  return out;
 }
 
 }  // namespace ttsa_host

@@ -582,6 +582,20 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       h_msched.clear();
     }
   }
+  // segment schedule of the same basis (host_tables.hpp): one read of every bin, two accumulators per cell; the default of the
+  // warp-stream feature kernel when the basis is a 50 %-overlap triangular bank (TTSA_FEAT_MEL=lane keeps the lane schedule)
+  std::vector<uint32_t> h_mseg;
+  p->geo.mel_seg_pairs[0] = p->geo.mel_seg_pairs[1] = p->geo.mel_seg_pairs[2] = 0;
+  {
+    const char* fm = std::getenv("TTSA_FEAT_MEL");
+    if (!(fm != nullptr && std::strcmp(fm, "lane") == 0)) {
+      ttsa_host::MelSegSchedule sc = ttsa_host::mel_segment_schedule(p->h_mel, c.num_mels, kF);
+      if (sc.ok) {
+        h_mseg.swap(sc.words);
+        for (int i = 0; i < 3; ++i) p->geo.mel_seg_pairs[i] = sc.pairs[i];
+      }
+    }
+  }
   p->pinv_chunks = (c.num_mels + kTcChunk - 1) / kTcChunk;
   const std::vector<uint16_t> h_pinv_tc = canon_split_b(p->h_inv_mel, kF, c.num_mels, 208, 5, p->pinv_chunks);
   std::vector<uint16_t> h_mel_tc;
@@ -601,7 +615,8 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       {h_pinv_tc96.data(), h_pinv_tc96.size() * 2, 0}, {h_img.data(), h_img.size() * 4, 0},
       {h_melc.data(), h_melc.size() * 4, 0}, {h_pw2.data(), h_pw2.size() * 4, 0}, {h_wps.data(), h_wps.size() * 4, 0},
       {h_edge_head.data(), h_edge_head.size() * 4, 0}, {h_edge_tail.data(), h_edge_tail.size() * 4, 0},
-      {h_msched.data(), h_msched.size() * 4, 0}, {h_pinv_tc128.data(), h_pinv_tc128.size() * 2, 0}};
+      {h_msched.data(), h_msched.size() * 4, 0}, {h_pinv_tc128.data(), h_pinv_tc128.size() * 2, 0},
+      {h_mseg.data(), h_mseg.size() * 4, 0}};
   size_t total = 0;
   for (auto& pc : pieces) { pc.off = total; total += (pc.bytes + 255) / 256 * 256; }
   if (cudaMalloc(&p->d_block, total) != cudaSuccess) {
@@ -629,6 +644,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
   p->tb.pw2 = (const float2*)(base + pieces[16].off);
   p->tb.wps_image = (const float*)(base + pieces[17].off);
   p->tb.mel_sched = h_msched.empty() ? nullptr : (const float*)(base + pieces[20].off);
+  p->tb.mel_seg = h_mseg.empty() ? nullptr : (const unsigned*)(base + pieces[22].off);
   p->tb.edge_head = (const float*)(base + pieces[18].off);
   p->tb.edge_tail = (const float*)(base + pieces[19].off);
   p->tb.mel_lo = (const int*)(base + pieces[5].off);
@@ -653,7 +669,7 @@ extern "C" int ttsa_plan_create(const ttsa_config* cfg, int device, ttsa_plan** 
       if (err) { cudaFree(p->d_block); delete p; return fail(TTSA_ERR_CUDA, "kernel configuration: %s", err); }
     }
   }
-  if (feat_stream_supported(c.hop_length, c.win_length, p->geo.mel_steps > 0 ? p->geo.mel_steps * 128 + 96 : p->geo.mel_smem_floats)) {
+  if (feat_stream_supported(c.hop_length, c.win_length, feat_mel_floats(p->geo))) {
     const char* fk = std::getenv("TTSA_FEAT_KERNEL");
     p->feat_stream = !(fk != nullptr && std::strcmp(fk, "tile") == 0);
     const char* wg = std::getenv("TTSA_WPS_GRID");
@@ -700,6 +716,18 @@ extern "C" int ttsa_plan_inv_mel_basis(const ttsa_plan* plan, double* host_out) 
   if (!plan || !host_out) return fail(TTSA_ERR_BAD_ARG, "null argument");
   std::memcpy(host_out, plan->h_inv_mel.data(), plan->h_inv_mel.size() * sizeof(double));
   return TTSA_OK;
+}
+
+extern "C" int64_t ttsa_plan_mel_schedule(const ttsa_plan* plan, int32_t* pairs_out, uint32_t* words_out, int64_t cap_words) {
+  if (!plan || !pairs_out) return fail(TTSA_ERR_BAD_ARG, "null argument");
+  const ttsa_host::MelSegSchedule sc = ttsa_host::mel_segment_schedule(plan->h_mel, plan->cfg.num_mels, plan->cfg.num_freq);
+  for (int i = 0; i < 3; ++i) pairs_out[i] = sc.ok ? sc.pairs[i] : 0;
+  if (!sc.ok) return 0;
+  if (words_out != nullptr) {
+    if ((int64_t)sc.words.size() > cap_words) return fail(TTSA_ERR_BAD_ARG, "schedule needs %zu words, buffer holds %lld", sc.words.size(), (long long)cap_words);
+    std::memcpy(words_out, sc.words.data(), sc.words.size() * 4);
+  }
+  return (int64_t)sc.words.size();
 }
 
 // Work partition of the warp-stream Griffin-Lim kernel: the flattened frame list (utterance after utterance) is cut into
