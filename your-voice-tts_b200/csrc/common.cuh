@@ -124,6 +124,37 @@ struct BatchDev {
 constexpr int kWpsWinStride = 20;           // floats per lane row of the warp-stream kernel's window tables (>= rows of a frame; stride / 4 odd)
 constexpr int kWpsWarps = TTSA_WPS_WARPS;   // warps per CTA (one CTA per SM) of the warp-stream Griffin-Lim kernel
 constexpr int kMelSegScratch = 196;         // floats per warp: 192 partial sums of the segment schedule, the zero cell, padding
+
+// Warp index as a value the compiler knows to be the same in all 32 lanes (a shuffle from lane 0): what derives from it
+// (the warp's run of frames, utterance bounds, buffer addresses, loop counters) can then live in uniform registers
+// instead of the 128 per-thread ones.  -DTTSA_WARP_UNIFORM=0 restores the plain tid >> 5, =1 broadcasts only the warp index.
+#ifndef TTSA_WARP_UNIFORM
+#define TTSA_WARP_UNIFORM 2
+#endif
+__device__ __forceinline__ int warp_index() {
+#if TTSA_WARP_UNIFORM
+  return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+#else
+  return (int)(threadIdx.x >> 5);
+#endif
+}
+// The same for a value every lane loaded from the same address (per-run scalars of the batch descriptor).
+__device__ __forceinline__ int uni(int v) {
+#if TTSA_WARP_UNIFORM >= 2
+  return __shfl_sync(0xffffffffu, v, 0);
+#else
+  return v;
+#endif
+}
+__device__ __forceinline__ long long uni(long long v) {
+#if TTSA_WARP_UNIFORM >= 2
+  const int lo = __shfl_sync(0xffffffffu, (int)(unsigned)(unsigned long long)v, 0);
+  const int hi = __shfl_sync(0xffffffffu, (int)((unsigned long long)v >> 32), 0);
+  return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
+#else
+  return v;
+#endif
+}
 // floats of the mel schedule (or compact basis) the warp-stream feature kernel keeps in shared memory
 __host__ __device__ inline int feat_mel_floats(const Geo& g) {
   if (g.mel_seg_pairs[0] > 0) return 160 * (g.mel_seg_pairs[0] + g.mel_seg_pairs[1] + g.mel_seg_pairs[2]) + 96 + kWpsWarps * kMelSegScratch;

@@ -45,7 +45,7 @@ feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameA
   using G = WpsGeo<HOP, WIN>;
   using FG = FeatGeo<HOP, WIN>;
   extern __shared__ __align__(16) float smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = warp_index();
   float* const buf = smem + warp * kBufFloats;
   const float4* const tw4 = reinterpret_cast<const float4*>(smem + FG::sm_tw);
   const float4* const g4 = reinterpret_cast<const float4*>(smem + FG::sm_g);
@@ -91,15 +91,15 @@ feat_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const FrameA
   int f = fa;
   while (f < fb) {
     while (bd.tsum[u + 1] <= f) ++u;                               // skips empty utterances
-    const int tsu = bd.tsum[u];
-    const int T = bd.T[u];
+    const int tsu = uni(bd.tsum[u]);
+    const int T = uni(bd.T[u]);
     const int t_begin = f - tsu;
     const int t_end = min(T, fb - tsu);
     f = tsu + t_end;
-    const int L = bd.wav_len[u];
+    const int L = uni(bd.wav_len[u]);
     if (L <= 0) continue;
-    const float* __restrict__ src = a.wav_in + bd.wav_off[u];
-    const long long row0 = bd.frame_off[u];
+    const float* __restrict__ src = a.wav_in + uni(bd.wav_off[u]);
+    const long long row0 = uni(bd.frame_off[u]);
 
     // span of frame t: raw samples [a0 - 2, a0 + WIN + 4), a0 = the frame's first sample made even.  0: inside the utterance
     // (one bulk copy), 1: first / last frames of a long utterance (the part that exists by a bulk copy, the mirrored part

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kWpsThreads, 1)
 gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev wp, const FrameArgs a) {
   using G = WpsGeo<HOP, WIN>;
   extern __shared__ __align__(16) float smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = warp_index();
   constexpr float kInvN = 1.0f / (float)kNfft;
   constexpr float kTiny = 1e-37f;
   constexpr float kPhaseEps = 1e-18f;
@@ -232,7 +232,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
                  ::"r"(dst), "l"(tb.wps_image), "r"(bytes), "r"(mbar) : "memory");
   }
   const int wi = blockIdx.x * kWpsWarps + warp;
-  const int fa = wp.cut[wi], fb = wp.cut[wi + 1];
+  const int fa = uni(wp.cut[wi]), fb = uni(wp.cut[wi + 1]);
   __syncthreads();                                                 // the mbarrier is initialised for everyone
   {
     unsigned done = 0;
@@ -260,7 +260,7 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
 #pragma unroll 1
   for (int it = 0; it < n_it; ++it) {
   const int epoch = a.wps_epoch + it;
-  int u = wp.u0[wi];                                               // utterance of frame fa (host-built)
+  int u = uni(wp.u0[wi]);                                            // utterance of frame fa (host-built)
   WPS_STAMP(0);
   if (it > 0 && fa < fb) {
     if (wp.tsum[u] < fa) {                                         // the range starts inside utterance u
@@ -277,17 +277,17 @@ gl_stream_kernel(const Geo g, const Tables tb, const BatchDev bd, const WpsDev w
   int f = fa;
   while (f < fb) {
     while (wp.tsum[u + 1] <= f) ++u;                               // skips empty utterances
-    const int tsu = wp.tsum[u];
-    const int T = bd.T[u];
+    const int tsu = uni(wp.tsum[u]);
+    const int T = uni(bd.T[u]);
     const int t_begin = f - tsu;
     const int t_end = min(T, fb - tsu);
     f = tsu + t_end;
-    const int L = bd.wav_len[u];
+    const int L = uni(bd.wav_len[u]);
     if (L <= 0) continue;
-    const long long woff = bd.wav_off[u];
+    const long long woff = uni(bd.wav_off[u]);
     const float* __restrict__ src = wav_rd + woff;
     float* __restrict__ dst = wav_wr + woff;
-    const float* spec_row0 = a.spec + bd.frame_off[u] * kF;
+    const float* spec_row0 = a.spec + uni(bd.frame_off[u]) * kF;
 
     // a run that starts inside the utterance leaves its first kZone samples as raw partial sums; the owner of the
     // frames before the cut finishes them at the end of its run
